@@ -1,0 +1,59 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol that
+include/ppnet_b200.h declares; the product never routes through the oracle."""
+import ctypes
+import os
+import re
+
+from ppnet_b200 import _lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _lib.exported_symbols()
+    assert len(names) >= 8
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_version_and_error_string():
+    L = _lib.lib()
+    assert L.ppnet_version() >= 100
+    assert isinstance(L.ppnet_last_error(), bytes)
+    assert _lib.launch_count() >= 0
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on CPU."""
+    L = _lib.lib()
+    rc = L.ppnet_segcheck_edage_f64(None, ctypes.c_int64(4), None, ctypes.c_int64(0), ctypes.c_int64(1), None,
+                                    None, ctypes.c_int32(0), ctypes.c_double(4.48), ctypes.c_double(224.0),
+                                    ctypes.c_int32(0), None, None)
+    assert rc == -1 and L.ppnet_last_error()
+    rc = L.ppnet_segcheck_edage_f64(None, ctypes.c_int64(0), None, ctypes.c_int64(0), ctypes.c_int64(0), None,
+                                    None, ctypes.c_int32(0), ctypes.c_double(4.48), ctypes.c_double(224.0),
+                                    ctypes.c_int32(7), None, None)
+    assert rc == -1          # bad dot_mode
+    rc = L.ppnet_grid_index_f64(None, ctypes.c_int64(0), ctypes.c_double(50), ctypes.c_double(224),
+                                ctypes.c_double(112), None, None)
+    assert rc == 0           # empty input is a no-op
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure; nothing under ppnet_b200/ may reference it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[./]_build|liboracle", re.M)
+    for root, _, files in os.walk(os.path.join(REPO, "ppnet_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                with open(os.path.join(root, f)) as fh:
+                    assert not pat.search(fh.read()), os.path.join(root, f)
+
+
+def test_ops_refuse_cpu_tensors():
+    import pytest
+    import torch
+
+    from ppnet_b200 import PPNetError, ops
+    with pytest.raises(PPNetError):
+        ops.grid_index_f64(torch.zeros(4, 2, dtype=torch.float64), 50, 224, 112)
