@@ -2,7 +2,7 @@
  *
  * The PPNet reference has no FFI layer: its boundary is a set of Python functions/methods
  * (SURVEY.md 8(b)).  Each entry point below replaces the numerical body of the reference
- * function cited beside it; `ppnet_b200/*.py` keeps the reference's Python names/signatures and
+ * function cited beside it; the modules under `ppnet_b200/` keep the reference's Python names/signatures and
  * binds these symbols with ctypes (see INTEGRATION.md for the stub a PPNet maintainer would add).
  *
  * Conventions
@@ -92,6 +92,105 @@ int ppnet_corridor_paint(const double* x0, const double* dir, const double* step
                          int64_t n_paths, int32_t rays_per_path, double map_size, double resolution,
                          double mapoffset, int32_t W, int32_t H, uint8_t value, uint8_t* space,
                          void* stream);
+
+/* ---- A6   Path.convexhull  EDaGe-PP/Path.py:388-395 (scipy.spatial.ConvexHull on integer cells)
+ *      pts[P][np][2] int32 -> hull[P][hmax][2] CCW from the lexicographically smallest vertex,
+ *      strict corners only; hull_cnt[P] (a value > hmax means the output was truncated).          */
+int ppnet_hull2d_i32(const int32_t* pts, int32_t np, int64_t n_paths, int32_t hmax, int32_t* hull,
+                     int32_t* hull_cnt, void* stream);
+
+/* ---- A10  Path.boundary_check(angle, translation)  EDaGe-PP/Path.py:100-111
+ *      hull[B][hmax][2] float64 (row, col), hull_cnt[B]; query i uses hull path_idx[i] (NULL -> 0),
+ *      angle_arg[i] (degrees, as passed to the method) and trans_arg[i][2].  ok[i] in {0,1};
+ *      hull_out[n][hmax][2] (may be NULL) receives the transformed vertices.                      */
+int ppnet_boundary_check(const double* hull, const int32_t* hull_cnt, int32_t hmax,
+                         const int32_t* path_idx, const double* angle_arg, const double* trans_arg,
+                         int64_t n, double resolution, uint8_t* ok, double* hull_out, void* stream);
+
+/* ---- counter-based sampling (Philox4x32-10); the reference draws from global MT19937 streams
+ *      (np.random / torch.rand), which cannot be sharded; parity is distributional.
+ *      out[u][k] = k-th uniform double in [0,1) of unit (unit0 + u) in sub-stream stream_id.     */
+int ppnet_uniform_f64(uint64_t seed, uint32_t stream_id, uint64_t unit0, int64_t n_units,
+                      int32_t per_unit, double* out, void* stream);
+
+/* ---- A17  GMM(order, dim, mean_range, std_range)  EDaGe-PP/GMM.py:7-16
+ *      gmm_params draws mean/std [order][dim] and weights [order] (float32, torch.rand-style);
+ *      gmm_sample = Distribution.sample([n]) -> out[n][dim] float32, comp[n] (may be NULL).       */
+int ppnet_gmm_params(uint64_t seed, int32_t order, int32_t dim, float mean_range, float std_range,
+                     float* mean, float* stdv, float* weights, void* stream);
+int ppnet_gmm_sample(uint64_t seed, uint64_t sample0, int64_t n, int32_t order, int32_t dim,
+                     const float* mean, const float* stdv, const float* weights, float* out,
+                     int32_t* comp, void* stream);
+
+/* ---- A15  plot_obstacles  EDaGe-PP/Path.py:36-49, restated geometrically (parity unpinned):
+ *      bits[M][R][ceil(R/32)] uint32, bit (j&31) of word (j>>5) of row i set iff the centre of
+ *      pixel (row i, col j) is inside a disk (x, y, r + inflate).                                 */
+int ppnet_raster_circles_bits(const double* obs, const int32_t* obs_cnt, int32_t omax,
+                              int64_t n_maps, int32_t resolution, double inflate, uint32_t* bits,
+                              void* stream);
+
+/* ---- integer DDA grid check (new functionality; endpoints snapped with the A4 rule).
+ *      segs_xy[N][4] float32 pixel coordinates grouped by map (CSR: pass the longest row in
+ *      segs_per_map).  verdict[i] = 1 if a visited cell is occupied or outside [0,R)^2;
+ *      first_hit[i] (may be NULL) = step index of that cell, -1 when free.                        */
+int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int64_t n_maps,
+                        const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
+                        int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit, void* stream);
+
+/* ---- A10 + A13 + A14 (+ A15): the fused map generator, one launch for n_maps maps.
+ *      MapGenerate.generate inner block EDaGe-PP/MapGenerate.py:58-124 and generate_map_randomly
+ *      :126-151.  Map g = map0 + i uses target path (g / reps) % n_bank  (index rule :68).        */
+typedef struct ppnet_gen_params {
+    /* target-path bank, device pointers */
+    const double* bank_pathpt;     /* [n_bank][np][2]     Path.PathPoint  (row, col)              */
+    const double* bank_segpt;      /* [n_bank][nseg1][2]  Path.SegPointImage                      */
+    const double* bank_hull;       /* [n_bank][hmax][2]   Path.ConvexHull                         */
+    const int32_t* bank_hull_cnt;  /* [n_bank]                                                    */
+    const double* bank_obs;        /* [n_bank][pomax][3]  Path.obstacles [x, y, r] (may be NULL)  */
+    const int32_t* bank_obs_cnt;   /* [n_bank]                                                    */
+    int32_t n_bank, np, nseg1, hmax, pomax;
+    /* what to generate */
+    int64_t map0, n_maps;
+    int32_t reps;                  /* maps per target path before moving on (= P in the reference) */
+    int32_t obstacles_num;         /* O  */
+    int32_t max_tries;             /* placement retry budget (reference guard: 10^6)               */
+    int32_t reserved0;
+    double resolution, map_size, obstacle_size, clearance, raster_inflate;
+    uint64_t seed;
+    /* optional caller-supplied draws (parity mode); NULL -> Philox keyed by the global map index  */
+    const double* in_angle;        /* [n_maps]      angle as drawn (degrees)                      */
+    const int32_t* in_trans;       /* [n_maps][2]   translation as drawn [t0, t1]                 */
+    const double* in_cand;         /* [n_maps][O][3] (x, y, r) in map units                       */
+    /* outputs (any may be NULL) */
+    double* out_angle;             /* [n_maps]                                                    */
+    int32_t* out_trans;            /* [n_maps][2]                                                 */
+    double* out_segpt;             /* [n_maps][nseg1][2]                                          */
+    double* out_pathpt;            /* [n_maps][np][2]                                             */
+    double* out_obs;               /* [n_maps][O + pomax][3] accepted random first, then path obs */
+    int32_t* out_obs_cnt;          /* [n_maps]                                                    */
+    int32_t* out_rand_cnt;         /* [n_maps] accepted random obstacles                          */
+    uint32_t* out_bits;            /* [n_maps][R][ceil(R/32)]                                     */
+    int32_t* out_tries;            /* [n_maps] placement tries used, 0 = budget exhausted         */
+    uint8_t* out_valid;            /* [n_maps]                                                    */
+    unsigned long long* counters;  /* [4] += maps_done, valid_paths, obstacles_accepted, tries    */
+} ppnet_gen_params;
+int ppnet_generate_maps(const ppnet_gen_params* params, void* stream);
+
+/* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
+int ppnet_ctx_create(int32_t device, void** ctx);
+int ppnet_ctx_destroy(void* ctx);
+int ppnet_ctx_bytes(void* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes);
+int ppnet_segcheck_edage_f64_host(void* ctx, const double* pts_rc, int64_t n_segs,
+                                  const int64_t* seg_off, int64_t segs_per_map, int64_t n_maps,
+                                  const double* obs, const int32_t* obs_cnt, int32_t omax,
+                                  double clearance, double bound, int32_t dot_mode, uint8_t* verdict);
+int ppnet_segcheck_mpnet_f32_host(void* ctx, const float* pts_xy, int64_t n_segs,
+                                  const int64_t* seg_off, int64_t segs_per_map, int64_t n_maps,
+                                  const double* obs, const int32_t* obs_cnt, int32_t omax,
+                                  double clearance, double bound, uint8_t* verdict, uint8_t* steer);
+int ppnet_clearance_filter_f64_host(void* ctx, const double* pathpt, int32_t np, const double* cand,
+                                    int32_t O, int64_t n_maps, double map_size, double resolution,
+                                    double clearance, uint8_t* accept, double* out, int32_t* out_cnt);
 
 #ifdef __cplusplus
 }

@@ -252,7 +252,7 @@ void orc_raster_circles_bits(const double* obs, const int32_t* obs_cnt, int omax
         for (int k = 0; k < obs_cnt[m]; ++k) {
             const double* o = obs + ((size_t)m * omax + k) * 3;
             double rr = o[2] + inflate;
-            if (!(rr > 0)) continue;
+            if (!(rr > 0) || !isfinite(rr) || !isfinite(o[0]) || !isfinite(o[1])) continue;
             double r2 = rr * rr;
             long i0 = (long)floor(o[1] - rr - 1), i1 = (long)ceil(o[1] + rr + 1);
             long j0 = (long)floor(o[0] - rr - 1), j1 = (long)ceil(o[0] + rr + 1);
@@ -271,6 +271,13 @@ void orc_raster_circles_bits(const double* obs, const int32_t* obs_cnt, int omax
     }
 }
 
+static inline int64_t snap_clamp(float v) {             /* A4 rule at step 1 / offset 0, clamped to +-2^29 */
+    double r = nearbyint((double)v);
+    if (r < -536870912.0) r = -536870912.0;
+    if (r > 536870912.0) r = 536870912.0;
+    return (int64_t)r;
+}
+
 static inline int64_t fdiv(int64_t a, int64_t b) {      /* floor division, b > 0 */
     int64_t q = a / b, r = a % b;
     return (r != 0 && r < 0) ? q - 1 : q;
@@ -281,10 +288,13 @@ void orc_dda_gridcheck(const uint32_t* bits, int R, const float* segs_xy, const 
     int W = (R + 31) / 32;
     for (long i = 0; i < n; ++i) {
         const uint32_t* b = bits + (size_t)seg_map[i] * R * W;
-        int64_t x0 = (int64_t)nearbyint((double)segs_xy[4 * i]);
-        int64_t y0 = (int64_t)nearbyint((double)segs_xy[4 * i + 1]);
-        int64_t x1 = (int64_t)nearbyint((double)segs_xy[4 * i + 2]);
-        int64_t y1 = (int64_t)nearbyint((double)segs_xy[4 * i + 3]);
+        const float* sg = segs_xy + 4 * i;
+        if (sg[0] != sg[0] || sg[1] != sg[1] || sg[2] != sg[2] || sg[3] != sg[3]) {   /* NaN: blocked at k = 0 */
+            verdict[i] = 1;
+            if (first_hit) first_hit[i] = 0;
+            continue;
+        }
+        int64_t x0 = snap_clamp(sg[0]), y0 = snap_clamp(sg[1]), x1 = snap_clamp(sg[2]), y1 = snap_clamp(sg[3]);
         int64_t dx = x1 - x0, dy = y1 - y0;
         int64_t nn = llabs(dx) > llabs(dy) ? llabs(dx) : llabs(dy);
         int hit = 0;

@@ -1,0 +1,117 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as
+1, 2, 3", SC'11; Random123 reference constants) and the draw layouts of the B200 generator kernels.
+Known-answer vectors (Random123 kat_vectors) are checked in tests/test_philox_cpu.py."""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+STREAM_PLACE, STREAM_OBST, STREAM_GMM_PARAM, STREAM_GMM_SAMPLE, STREAM_UNIFORM, STREAM_PATH = 1, 2, 3, 4, 5, 6
+
+
+def philox4x32_10(key, ctr):
+    """key (k0, k1) ints; ctr uint32[n,4] -> uint32[n,4]."""
+    c = np.asarray(ctr, dtype=np.uint64).reshape(-1, 4).copy()
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c[:, 0]
+        p1 = M1 * c[:, 2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        n0 = hi1 ^ c[:, 1] ^ np.uint64(k0)
+        n2 = hi0 ^ c[:, 3] ^ np.uint64(k1)
+        c = np.stack([n0, lo1, n2, lo0], axis=1)
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return c.astype(np.uint32)
+
+
+def key_of(seed):
+    return (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+
+
+def u53(a, b):
+    """53-bit double in [0,1) from two words (numpy random_sample construction)."""
+    a = np.asarray(a, dtype=np.uint64)
+    b = np.asarray(b, dtype=np.uint64)
+    return ((a >> np.uint64(5)) * np.uint64(1 << 26) + (b >> np.uint64(6))).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def u24(a):
+    return (np.asarray(a, dtype=np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def _ctr(block, stream, unit):
+    block = np.asarray(block, dtype=np.uint64).reshape(-1)
+    unit = np.broadcast_to(np.asarray(unit, dtype=np.uint64), block.shape)
+    return np.stack([block, np.full(block.shape, stream, dtype=np.uint64), unit & MASK, unit >> np.uint64(32)], axis=1)
+
+
+def uniform(seed, stream, unit0, n_units, per_unit):
+    """ppnet_uniform_f64: out[u][k]; block = k//2, words (x,y) for even k, (z,w) for odd k."""
+    out = np.empty([n_units, per_unit])
+    nb = (per_unit + 1) // 2
+    for u in range(n_units):
+        r = philox4x32_10(key_of(seed), _ctr(np.arange(nb), stream, unit0 + u))
+        vals = np.stack([u53(r[:, 0], r[:, 1]), u53(r[:, 2], r[:, 3])], axis=1).reshape(-1)
+        out[u] = vals[:per_unit]
+    return out
+
+
+def placement_draw(seed, g, t, resolution):
+    """Try t of map g -> (angle_deg, t0, t1):  MapGenerate.py:63-64 applied to Philox uniforms."""
+    r = philox4x32_10(key_of(seed), _ctr([2 * t, 2 * t + 1], STREAM_PLACE, g))
+    R = np.float64(resolution)
+    angle = u53(r[0, 0], r[0, 1]) * 360 - 180
+    t0 = int(u53(r[0, 2], r[0, 3]) * R - R / 2)
+    t1 = int(u53(r[1, 0], r[1, 1]) * R - R / 2)
+    return float(angle), t0, t1
+
+
+def candidates(seed, g, O, map_size, obstacle_size):
+    """cand[O,3] = (x, y, r) map units: block j -> (x, y); block O + j//2, half j&1 -> r."""
+    a = philox4x32_10(key_of(seed), _ctr(np.arange(O), STREAM_OBST, g))
+    b = philox4x32_10(key_of(seed), _ctr(O + np.arange((O + 1) // 2), STREAM_OBST, g))
+    x = u53(a[:, 0], a[:, 1]) * np.float64(map_size)
+    y = u53(a[:, 2], a[:, 3]) * np.float64(map_size)
+    rr = np.stack([u53(b[:, 0], b[:, 1]), u53(b[:, 2], b[:, 3])], axis=1).reshape(-1)[:O]
+    return np.stack([x, y, rr * np.float64(obstacle_size)], axis=1)
+
+
+def gmm_params(seed, order, dim, mean_range, std_range):
+    r = philox4x32_10(key_of(seed), _ctr(np.arange(order * dim), STREAM_GMM_PARAM, 0))
+    mean = (u24(r[:, 0]) * np.float32(mean_range)).reshape(order, dim)
+    std = (u24(r[:, 1]) * np.float32(std_range)).reshape(order, dim)
+    w = u24(r[:order, 2])
+    return mean, std, w
+
+
+def gmm_sample(seed, sample0, n, mean, std, w):
+    """dim <= 2 layout: block 0 of sample i: x -> component, (y, z) -> Box-Muller pair (float32 math;
+    the device uses logf / sincospif, so values agree to ~1e-5 relative, components exactly)."""
+    K, D = mean.shape
+    assert D <= 2
+    r = philox4x32_10(key_of(seed), _ctr(np.zeros(n), STREAM_GMM_SAMPLE, sample0 + np.arange(n, dtype=np.uint64)))
+    tot = np.float32(0)
+    for k in range(K):
+        tot = np.float32(tot + w[k])
+    cdf = np.empty(K, dtype=np.float32)
+    acc = np.float32(0)
+    for k in range(K):
+        acc = np.float32(acc + w[k])
+        cdf[k] = np.float32(acc / tot)
+    uc = u24(r[:, 0])
+    comp = np.minimum((uc[:, None] >= cdf[None, :]).sum(axis=1), K - 1)
+    # `while k < K-1 and uc >= cdf[k]` stops at the first k with uc < cdf[k]; cdf is non-decreasing
+    comp = np.asarray([next((k for k in range(K - 1) if not uc[i] >= cdf[k]), K - 1) for i in range(n)]) if n <= 4096 else comp
+    u1 = ((r[:, 1] >> np.uint32(8)).astype(np.float32) + np.float32(1)) * np.float32(1.0 / 16777216.0)
+    u2 = u24(r[:, 2])
+    rad = np.sqrt(np.float32(-2) * np.log(u1)).astype(np.float32)
+    z0 = rad * np.cos(np.float32(2 * np.pi) * u2).astype(np.float32)
+    z1 = rad * np.sin(np.float32(2 * np.pi) * u2).astype(np.float32)
+    out = np.empty([n, D], dtype=np.float32)
+    out[:, 0] = mean[comp, 0] + std[comp, 0] * z0
+    if D > 1:
+        out[:, 1] = mean[comp, 1] + std[comp, 1] * z1
+    return out, comp.astype(np.int32)

@@ -569,7 +569,7 @@ def raster_circles_bits(obs, resolution, inflate=0.0):
     jj = np.arange(R, dtype=np.float64) + 0.5
     for ox, oy, r in obs:
         rr = f64(r) + f64(inflate)
-        if not rr > 0:
+        if not rr > 0 or not np.isfinite(rr) or not np.isfinite(ox) or not np.isfinite(oy):
             continue
         r2 = rr * rr
         for i in range(max(0, int(math.floor(oy - rr - 1))), min(R, int(math.ceil(oy + rr + 1)))):
@@ -587,26 +587,36 @@ def raster_circles_bits(obs, resolution, inflate=0.0):
 # DDA walks the major axis one cell at a time; minor = start + round_half_up(k*dminor/dmajor)
 # computed in integers.  Verdict: first visited cell that is out of [0,R)^2 or occupied.
 # --------------------------------------------------------------------------------------------
+DDA_CLAMP = 1 << 29
+
+
+def _snap(v):
+    """A4 rule at step 1 / offset 0: rint half-to-even, clamped to +-2^29.  NaN -> None."""
+    v = float(v)
+    if v != v:
+        return None
+    return int(min(max(np.rint(f64(v)), -DDA_CLAMP), DDA_CLAMP))
+
+
 def dda_cells(s_xy, e_xy):
-    x0, y0 = int(np.rint(f64(s_xy[0]))), int(np.rint(f64(s_xy[1])))
-    x1, y1 = int(np.rint(f64(e_xy[0]))), int(np.rint(f64(e_xy[1])))
+    """Generator of the visited cells (x, y), k = 0 .. n."""
+    x0, y0, x1, y1 = _snap(s_xy[0]), _snap(s_xy[1]), _snap(e_xy[0]), _snap(e_xy[1])
     dx, dy = x1 - x0, y1 - y0
     n = max(abs(dx), abs(dy))
-    cells = []
+    if n == 0:
+        yield (x0, y0)
+        return
     for k in range(n + 1):
-        if n == 0:
-            cells.append((x0, y0))
-            break
         # round-half-up of k*d/n in integers: floor((2*k*d + n) / (2n))
-        cx = x0 + (2 * k * dx + n) // (2 * n)
-        cy = y0 + (2 * k * dy + n) // (2 * n)
-        cells.append((cx, cy))
-    return cells
+        yield (x0 + (2 * k * dx + n) // (2 * n), y0 + (2 * k * dy + n) // (2 * n))
 
 
 def dda_gridcheck(bits, resolution, s_xy, e_xy):
-    """Returns (hit bool, first_hit_index int) -- index = k of the first blocked cell, -1 if free."""
+    """Returns (hit bool, first_hit_index int) -- index = k of the first blocked cell, -1 if free.
+    A NaN coordinate is blocked at k = 0."""
     R = int(resolution)
+    if any(float(v) != float(v) for v in (s_xy[0], s_xy[1], e_xy[0], e_xy[1])):
+        return True, 0
     for k, (cx, cy) in enumerate(dda_cells(s_xy, e_xy)):
         if cx < 0 or cx >= R or cy < 0 or cy >= R:
             return True, k

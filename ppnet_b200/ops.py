@@ -153,3 +153,193 @@ def corridor_paint(x0, dirs, step_num, map_size, resolution, mapoffset, width, h
                                      ctypes.c_double(mapoffset), ctypes.c_int32(width), ctypes.c_int32(height),
                                      ctypes.c_uint8(value), _ptr(space), _stream()), "ppnet_corridor_paint")
     return space
+
+
+# ------------------------------------------------------------------------------------------------
+STREAM_PLACE, STREAM_OBST, STREAM_GMM_PARAM, STREAM_GMM_SAMPLE, STREAM_UNIFORM, STREAM_PATH = 1, 2, 3, 4, 5, 6
+DEFAULT_SEED = 0x5050_4E45_54          # "PPNET"
+
+
+def hull2d_i32(pts, hmax=64):
+    """A6 batched (EDaGe-PP/Path.py:388-395): pts i32[P,Np,2] -> (hull i32[P,hmax,2] CCW, cnt i32[P])."""
+    _need(pts, torch.int32, "pts")
+    p, np_, _ = pts.shape
+    hull = torch.zeros([p, hmax, 2], dtype=torch.int32, device=pts.device)
+    cnt = torch.empty(p, dtype=torch.int32, device=pts.device)
+    check(lib().ppnet_hull2d_i32(_ptr(pts), ctypes.c_int32(np_), ctypes.c_int64(p), ctypes.c_int32(hmax), _ptr(hull),
+                                 _ptr(cnt), _stream()), "ppnet_hull2d_i32")
+    return hull, cnt
+
+
+def boundary_check(hull, hull_cnt, path_idx, angle_arg, trans_arg, resolution, want_hull=False):
+    """A10 batched (EDaGe-PP/Path.py:100-111): hull f64[B,hmax,2], queries (path_idx i32[N] or None,
+    angle_arg f64[N] degrees as passed to the method, trans_arg f64[N,2]) -> ok u8[N] (, hull' f64[N,hmax,2])."""
+    _need(hull, torch.float64, "hull")
+    _need(hull_cnt, torch.int32, "hull_cnt")
+    _need(angle_arg, torch.float64, "angle_arg")
+    _need(trans_arg, torch.float64, "trans_arg")
+    if path_idx is not None:
+        _need(path_idx, torch.int32, "path_idx")
+    n, hmax = angle_arg.numel(), hull.shape[1]
+    ok = torch.empty(n, dtype=torch.uint8, device=hull.device)
+    ho = torch.zeros([n, hmax, 2], dtype=torch.float64, device=hull.device) if want_hull else None
+    check(lib().ppnet_boundary_check(_ptr(hull), _ptr(hull_cnt), ctypes.c_int32(hmax), _ptr(path_idx), _ptr(angle_arg),
+                                     _ptr(trans_arg), ctypes.c_int64(n), ctypes.c_double(resolution), _ptr(ok), _ptr(ho),
+                                     _stream()), "ppnet_boundary_check")
+    return (ok, ho) if want_hull else ok
+
+
+def uniform_f64(seed, stream_id, unit0, n_units, per_unit, device="cuda"):
+    """Philox4x32-10 uniforms: f64[n_units, per_unit] in [0,1), a pure function of (seed, stream, unit, k)."""
+    out = torch.empty([n_units, per_unit], dtype=torch.float64, device=device)
+    check(lib().ppnet_uniform_f64(ctypes.c_uint64(seed), ctypes.c_uint32(stream_id), ctypes.c_uint64(unit0),
+                                  ctypes.c_int64(n_units), ctypes.c_int32(per_unit), _ptr(out), _stream()),
+          "ppnet_uniform_f64")
+    return out
+
+
+def gmm_params(seed, order=10, dim=2, mean_range=70.0, std_range=5.0, device="cuda"):
+    """A17 GMM.__init__ draws (EDaGe-PP/GMM.py:11-13) -> (mean f32[K,D], std f32[K,D], weights f32[K])."""
+    mean = torch.empty([order, dim], dtype=torch.float32, device=device)
+    std = torch.empty([order, dim], dtype=torch.float32, device=device)
+    w = torch.empty([order], dtype=torch.float32, device=device)
+    check(lib().ppnet_gmm_params(ctypes.c_uint64(seed), ctypes.c_int32(order), ctypes.c_int32(dim),
+                                 ctypes.c_float(mean_range), ctypes.c_float(std_range), _ptr(mean), _ptr(std), _ptr(w),
+                                 _stream()), "ppnet_gmm_params")
+    return mean, std, w
+
+
+def gmm_sample(seed, sample0, n, mean, std, weights, want_comp=False, out=None):
+    """A17 Distribution.sample([n]) (EDaGe-PP/GMM.py:14-16) -> f32[n, D] (, comp i32[n])."""
+    _need(mean, torch.float32, "mean")
+    _need(std, torch.float32, "std")
+    _need(weights, torch.float32, "weights")
+    k, d = mean.shape
+    out = torch.empty([n, d], dtype=torch.float32, device=mean.device) if out is None else _need(out, torch.float32, "out")
+    comp = torch.empty([n], dtype=torch.int32, device=mean.device) if want_comp else None
+    check(lib().ppnet_gmm_sample(ctypes.c_uint64(seed), ctypes.c_uint64(sample0), ctypes.c_int64(n), ctypes.c_int32(k),
+                                 ctypes.c_int32(d), _ptr(mean), _ptr(std), _ptr(weights), _ptr(out), _ptr(comp),
+                                 _stream()), "ppnet_gmm_sample")
+    return (out, comp) if want_comp else out
+
+
+def raster_circles_bits(obs, obs_cnt, resolution, inflate=0.0, out=None):
+    """A15 restated: obs f64[M,omax,3], obs_cnt i32[M] -> bits u32 (as int32 tensor) [M,R,ceil(R/32)]."""
+    _need(obs, torch.float64, "obs")
+    _need(obs_cnt, torch.int32, "obs_cnt")
+    m, omax, _ = obs.shape
+    w = (resolution + 31) // 32
+    bits = torch.empty([m, resolution, w], dtype=torch.int32, device=obs.device) if out is None else out
+    check(lib().ppnet_raster_circles_bits(_ptr(obs), _ptr(obs_cnt), ctypes.c_int32(omax), ctypes.c_int64(m),
+                                          ctypes.c_int32(resolution), ctypes.c_double(inflate), _ptr(bits), _stream()),
+          "ppnet_raster_circles_bits")
+    return bits
+
+
+def dda_gridcheck(bits, resolution, segs_xy, seg_off=None, want_first=True, max_segs_per_map=None):
+    """Integer DDA vs bit-packed maps: bits i32[M,R,W], segs f32[N,4] grouped by map -> (verdict u8[N], first i32[N])."""
+    _need(bits, torch.int32, "bits")
+    _need(segs_xy, torch.float32, "segs_xy")
+    m, n = bits.shape[0], segs_xy.shape[0]
+    if seg_off is None:
+        so, spm = None, n // max(m, 1)
+    else:
+        so = _need(seg_off, torch.int64, "seg_off")
+        spm = max_segs_per_map if max_segs_per_map is not None else max(int((so[1:] - so[:-1]).max().item()), 1)
+    v = torch.empty(n, dtype=torch.uint8, device=bits.device)
+    fh = torch.empty(n, dtype=torch.int32, device=bits.device) if want_first else None
+    check(lib().ppnet_dda_gridcheck(_ptr(bits), ctypes.c_int32(resolution), ctypes.c_int64(m), _ptr(segs_xy),
+                                    ctypes.c_int64(n), _ptr(so), ctypes.c_int64(spm), _ptr(v), _ptr(fh), _stream()),
+          "ppnet_dda_gridcheck")
+    return (v, fh) if want_first else v
+
+
+class GenParams(ctypes.Structure):
+    """Mirror of `ppnet_gen_params` (include/ppnet_b200.h)."""
+    _fields_ = [
+        ("bank_pathpt", ctypes.c_void_p), ("bank_segpt", ctypes.c_void_p), ("bank_hull", ctypes.c_void_p),
+        ("bank_hull_cnt", ctypes.c_void_p), ("bank_obs", ctypes.c_void_p), ("bank_obs_cnt", ctypes.c_void_p),
+        ("n_bank", ctypes.c_int32), ("np", ctypes.c_int32), ("nseg1", ctypes.c_int32), ("hmax", ctypes.c_int32),
+        ("pomax", ctypes.c_int32),
+        ("map0", ctypes.c_int64), ("n_maps", ctypes.c_int64),
+        ("reps", ctypes.c_int32), ("obstacles_num", ctypes.c_int32), ("max_tries", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
+        ("resolution", ctypes.c_double), ("map_size", ctypes.c_double), ("obstacle_size", ctypes.c_double),
+        ("clearance", ctypes.c_double), ("raster_inflate", ctypes.c_double),
+        ("seed", ctypes.c_uint64),
+        ("in_angle", ctypes.c_void_p), ("in_trans", ctypes.c_void_p), ("in_cand", ctypes.c_void_p),
+        ("out_angle", ctypes.c_void_p), ("out_trans", ctypes.c_void_p), ("out_segpt", ctypes.c_void_p),
+        ("out_pathpt", ctypes.c_void_p), ("out_obs", ctypes.c_void_p), ("out_obs_cnt", ctypes.c_void_p),
+        ("out_rand_cnt", ctypes.c_void_p), ("out_bits", ctypes.c_void_p), ("out_tries", ctypes.c_void_p),
+        ("out_valid", ctypes.c_void_p), ("counters", ctypes.c_void_p),
+    ]
+
+
+class PathBank:
+    """Device-resident target-path bank consumed by generate_maps (what PathGroup.generate produces):
+    PathPoint f64[B,Np,2], SegPointImage f64[B,S+1,2], ConvexHull f64[B,hmax,2] + cnt, obstacles f64[B,pomax,3] + cnt."""
+
+    def __init__(self, pathpt, segpt, hull, hull_cnt, obs=None, obs_cnt=None, length=None):
+        self.pathpt = _need(pathpt, torch.float64, "pathpt")
+        self.segpt = _need(segpt, torch.float64, "segpt")
+        self.hull = _need(hull, torch.float64, "hull")
+        self.hull_cnt = _need(hull_cnt, torch.int32, "hull_cnt")
+        b = pathpt.shape[0]
+        if obs is None:
+            obs = torch.zeros([b, 1, 3], dtype=torch.float64, device=pathpt.device)
+            obs_cnt = torch.zeros([b], dtype=torch.int32, device=pathpt.device)
+        self.obs = _need(obs, torch.float64, "obs")
+        self.obs_cnt = _need(obs_cnt, torch.int32, "obs_cnt")
+        self.length = length
+        self.n_bank, self.np, self.nseg1 = b, pathpt.shape[1], segpt.shape[1]
+        self.hmax, self.pomax = hull.shape[1], self.obs.shape[1]
+
+
+class MapBatch:
+    """Outputs of one generate_maps launch (device tensors)."""
+    __slots__ = ("angle", "trans", "segpt", "pathpt", "obs", "obs_cnt", "rand_cnt", "bits", "tries", "valid",
+                 "counters", "map0", "n_maps")
+
+
+def generate_maps(bank, map0, n_maps, reps, obstacles_num, resolution=224, map_size=50.0, obstacle_size=5.0,
+                  clearance=1.0, seed=DEFAULT_SEED, max_tries=4096, want_bits=True, raster_inflate=0.0,
+                  in_angle=None, in_trans=None, in_cand=None, out=None, counters=None, want_labels=True):
+    """Fused A10+A13+A14(+A15) generator (EDaGe-PP/MapGenerate.py:58-151): one launch, one CTA per map.
+    Deterministic in (seed, global map index): any split of [map0, map0+n_maps) over ranks gives the same maps."""
+    dev_ = bank.pathpt.device
+    R, O = int(resolution), int(obstacles_num)
+    if out is None:
+        out = MapBatch()
+        out.angle = torch.empty([n_maps], dtype=torch.float64, device=dev_)
+        out.trans = torch.empty([n_maps, 2], dtype=torch.int32, device=dev_)
+        out.segpt = torch.empty([n_maps, bank.nseg1, 2], dtype=torch.float64, device=dev_) if want_labels else None
+        out.pathpt = torch.empty([n_maps, bank.np, 2], dtype=torch.float64, device=dev_) if want_labels else None
+        out.obs = torch.zeros([n_maps, O + bank.pomax, 3], dtype=torch.float64, device=dev_)
+        out.obs_cnt = torch.empty([n_maps], dtype=torch.int32, device=dev_)
+        out.rand_cnt = torch.empty([n_maps], dtype=torch.int32, device=dev_)
+        out.bits = torch.empty([n_maps, R, (R + 31) // 32], dtype=torch.int32, device=dev_) if want_bits else None
+        out.tries = torch.empty([n_maps], dtype=torch.int32, device=dev_)
+        out.valid = torch.empty([n_maps], dtype=torch.uint8, device=dev_)
+        out.counters = counters if counters is not None else torch.zeros([4], dtype=torch.int64, device=dev_)
+    out.map0, out.n_maps = map0, n_maps
+    if in_angle is not None:
+        _need(in_angle, torch.float64, "in_angle")
+        _need(in_trans, torch.int32, "in_trans")
+    if in_cand is not None:
+        _need(in_cand, torch.float64, "in_cand")
+    p = GenParams()
+    p.bank_pathpt, p.bank_segpt, p.bank_hull = bank.pathpt.data_ptr(), bank.segpt.data_ptr(), bank.hull.data_ptr()
+    p.bank_hull_cnt, p.bank_obs, p.bank_obs_cnt = bank.hull_cnt.data_ptr(), bank.obs.data_ptr(), bank.obs_cnt.data_ptr()
+    p.n_bank, p.np, p.nseg1, p.hmax, p.pomax = bank.n_bank, bank.np, bank.nseg1, bank.hmax, bank.pomax
+    p.map0, p.n_maps, p.reps, p.obstacles_num, p.max_tries = map0, n_maps, reps, O, max_tries
+    p.resolution, p.map_size, p.obstacle_size, p.clearance = float(R), float(map_size), float(obstacle_size), float(clearance)
+    p.raster_inflate, p.seed = float(raster_inflate), seed
+    p.in_angle = in_angle.data_ptr() if in_angle is not None else None
+    p.in_trans = in_trans.data_ptr() if in_trans is not None else None
+    p.in_cand = in_cand.data_ptr() if in_cand is not None else None
+    for name in ("angle", "trans", "segpt", "pathpt", "obs", "obs_cnt", "rand_cnt", "bits", "tries", "valid"):
+        t = getattr(out, name)
+        setattr(p, "out_" + name, t.data_ptr() if t is not None else None)
+    p.counters = out.counters.data_ptr()
+    check(lib().ppnet_generate_maps(ctypes.byref(p), _stream()), "ppnet_generate_maps")
+    return out
