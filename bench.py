@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- EDaGe-PP hot path on B200 (BASELINE.json metric: collision-checked segments/sec and valid
+paths/sec vs host CPU).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                   (CPU arm: the oracle port on the host cores)
+
+One step = one pass of the hot path over one batch of `--maps` synthetic maps per GPU (config 2: 10 000 maps,
+R=224, O=50 candidate circles, 1024 segments/map, clearance 1 -> 4.48 px):
+  generate_maps (placement rejection + label transform + obstacle draws + clearance verdict + bit raster)
+  -> segcheck f64 (A11) -> segcheck f32 (A12) -> integer DDA vs the bit-packed maps -> GMM samples.
+`value` is device-resident throughput (inputs already in HBM); `e2e` runs the same step through the
+host-buffer C ABI with pinned HOST inputs/outputs, copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+CLEAR_UNITS = 1.0                 # MapGenerate ctor default clearance (map units) -> 4.48 px at R=224, M=50
+R, MAP_SIZE, O, SEGS_PER_MAP, OBST_SIZE = 224, 50.0, 50, 1024, 5.0
+GMM_PER_MAP = 1000                # 10 M samples at 10 k maps
+N_BANK, REPS = 100, 10
+SEED = 0x5050_4E45_54
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_baseline(sample_maps, threads, python_port_segments=1500):
+    """The oracle timed on the host cores over a bounded sample of the same workload.  kind = "port"
+    (the reference is Python and cannot travel; oracle/ is its pinned restatement)."""
+    from oracle import c_oracle
+    from oracle import ppnet_oracle as orc
+    from ppnet_b200.synthetic import synthetic_bank, synthetic_segments
+
+    rng = np.random.default_rng(123)
+    bank = synthetic_bank(8, seed=1)
+    segs = synthetic_segments(sample_maps, SEGS_PER_MAP, seed=9)
+    seg_map = np.repeat(np.arange(sample_maps, dtype=np.int32), SEGS_PER_MAP)
+    obs = np.zeros([sample_maps, O, 3])
+    obs[..., 0] = rng.uniform(0, R, (sample_maps, O))
+    obs[..., 1] = rng.uniform(0, R, (sample_maps, O))
+    obs[..., 2] = rng.uniform(0, 22.4, (sample_maps, O))
+    cnt = rng.integers(20, O + 1, sample_maps).astype(np.int32)
+    clear_px = CLEAR_UNITS / MAP_SIZE * R
+    segs32 = segs.astype(np.float32)
+    pp = bank["pathpt"][rng.integers(0, 8, sample_maps)]
+    cand = np.stack([rng.uniform(0, 50, (sample_maps, O)), rng.uniform(0, 50, (sample_maps, O)),
+                     rng.uniform(0, 5, (sample_maps, O))], axis=2)
+    c_oracle.lib()
+    t0 = time.perf_counter()
+    c_oracle.clearance_filter(pp, cand, MAP_SIZE, R, CLEAR_UNITS, threads=threads)
+    bits = c_oracle.raster_circles_bits(obs, cnt, R, clear_px / 2, threads=threads)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    v64 = c_oracle.segcheck_f64(segs, seg_map, obs, cnt, clear_px, threads=threads)
+    c_oracle.segcheck_f32(segs32, seg_map, obs, cnt, clear_px, threads=threads, want_steer=False)
+    c_oracle.dda_gridcheck(bits, R, segs32, seg_map, threads=threads)
+    t_seg = time.perf_counter() - t0
+    n_seg = 3 * len(segs)
+    # the reference-style scalar Python path (numpy scalars, one segment at a time), 1 core
+    n_py = min(python_port_segments, len(segs))
+    t0 = time.perf_counter()
+    for i in range(n_py):
+        m = seg_map[i]
+        orc.segcheck_edage_f64(segs[i, :2], segs[i, 2:], obs[m, :cnt[m]].tolist(), clear_px)
+    t_py = time.perf_counter() - t0
+    return {"value": n_seg / (t_seg + t_gen), "unit": "segments/s", "cores": threads, "kind": "port",
+            "sample": "%d maps x %d segments x {A11 f64, A12 f32, DDA} + clearance filter + raster of those maps, "
+                      "plain-C oracle on %d threads" % (sample_maps, SEGS_PER_MAP, threads),
+            "valid_paths_per_s": sample_maps / (t_seg + t_gen),
+            "segcheck_only_segments_per_s": n_seg / t_seg,
+            "python_port_1core_segments_per_s": n_py / t_py, "positives": float(v64.mean())}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_maps = 256
+    for _ in range(max(args.warmup, 1)):
+        cpu_baseline(32, threads, python_port_segments=50)
+    t0 = time.perf_counter()
+    vals = [cpu_baseline(sample_maps, threads, python_port_segments=300) for _ in range(args.steps)]
+    dt = time.perf_counter() - t0
+    v = float(np.mean([x["value"] for x in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = v
+    line = {"impl": "reference", "metric": "collision-checked segments/sec", "value": v, "unit": "segments/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32+u32",
+            "data": "synthetic", "valid_paths_per_s": float(np.mean([x["valid_paths_per_s"] for x in vals])),
+            "config": {"workload": "config2: EDaGe-PP map generation + segment checks, bounded sample of %d maps per "
+                                   "step (R=224, O=50, 1024 segments/map, clearance 1)" % sample_maps},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from ppnet_b200 import _lib, host, ops
+    from ppnet_b200.synthetic import synthetic_bank, synthetic_segments
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M = args.maps
+    n_seg = M * SEGS_PER_MAP
+    clear_px = CLEAR_UNITS / MAP_SIZE * R
+
+    # ---- inputs (untimed): target-path bank, segments (host pinned + device), GMM parameters
+    bk = synthetic_bank(N_BANK, seed=0)
+    bank = ops.PathBank(*[torch.from_numpy(bk[k]).to(dev) for k in ("pathpt", "segpt", "hull", "hull_cnt", "obs", "obs_cnt")])
+    segs64_h = torch.from_numpy(synthetic_segments(M, SEGS_PER_MAP, seed=100 + rank)).pin_memory()
+    segs32_h = segs64_h.to(torch.float32).pin_memory()
+    segs64, segs32 = segs64_h.to(dev), segs32_h.to(dev)
+    g_mean, g_std, g_w = ops.gmm_params(SEED, 10, 2, 70.0, 5.0, device=dev)
+    n_gmm = GMM_PER_MAP * M
+    gmm_out = torch.empty([n_gmm, 2], dtype=torch.float32, device=dev)
+    v64 = torch.empty(n_seg, dtype=torch.uint8, device=dev)
+    v32 = torch.empty(n_seg, dtype=torch.uint8, device=dev)
+    counters = torch.zeros([4], dtype=torch.int64, device=dev)
+    gen = ops.generate_maps(bank, rank * M, M, REPS, O, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED, counters=counters,
+                            raster_inflate=clear_px / 2)
+    names = ["generate_maps", "segcheck_f64", "segcheck_f32", "dda_gridcheck", "gmm_sample"]
+
+    def step(it, ev=None):
+        map0 = (it * world + rank) * M                       # every step generates NEW maps (global index range)
+        if ev: ev[0].record()
+        ops.generate_maps(bank, map0, M, REPS, O, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED, out=gen,
+                          raster_inflate=clear_px / 2)
+        if ev: ev[1].record()
+        ops.segcheck_edage_f64(segs64, gen.obs, gen.obs_cnt, clear_px, out=v64)
+        if ev: ev[2].record()
+        ops.segcheck_mpnet_f32(segs32, gen.obs, gen.obs_cnt, clear_px, out=v32)
+        if ev: ev[3].record()
+        vd = ops.dda_gridcheck(gen.bits, R, segs32, want_first=False)
+        if ev: ev[4].record()
+        ops.gmm_sample(SEED, map0 * GMM_PER_MAP, n_gmm, g_mean, g_std, g_w, out=gmm_out)
+        if ev: ev[5].record()
+        return vd
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for it in range(args.warmup):
+        step(it)
+    barrier()
+    counters.zero_()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for it in range(args.steps):
+        vd = step(args.warmup + it, evs[it])
+    t_end.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        allc = [torch.zeros_like(counters) for _ in range(world)]
+        dist.all_gather(allc, counters)                      # the path's only collective: int64[4] per rank
+        tot = torch.stack(allc).sum(0).cpu().numpy()
+    else:
+        tot = counters.cpu().numpy()
+    ms_step = ms_total / args.steps
+    k_ms = np.asarray([[e[i].elapsed_time(e[i + 1]) for i in range(5)] for e in evs]).mean(axis=0)
+    maps_done, valid, acc_obs, tries = (int(x) for x in tot)
+    seg_per_step = 3 * n_seg * world
+    value = seg_per_step / (ms_step * 1e-3)
+    valid_per_s = valid / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes per launch / its mean launch duration)
+    avg_cnt = float(gen.obs_cnt.double().mean().item())
+    bits_b = R * ((R + 31) // 32) * 4
+    alg = {
+        "generate_maps": M * (16 * bank.np + 16 * bank.nseg1 + 8 + 8 + 24 * avg_cnt + bits_b + 13),
+        "segcheck_f64": n_seg * 33 + M * 24 * avg_cnt,
+        "segcheck_f32": n_seg * 17 + M * 24 * avg_cnt,
+        "dda_gridcheck": M * bits_b + n_seg * 17,
+        "gmm_sample": n_gmm * 8,
+    }
+    peak, peak_src = peaks()
+    kernels = {n: {"ms": float(k_ms[i]), "share": float(k_ms[i] / k_ms.sum()), "alg_bytes": float(alg[n]),
+                   "achieved_gbs": float(alg[n] / (k_ms[i] * 1e-3) / 1e9), "frac": float(alg[n] / (k_ms[i] * 1e-3) / 1e9 / peak)}
+               for i, n in enumerate(names)}
+    dom = names[int(np.argmax(k_ms))]
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "note": "analytic f64 verdict kernels are FP64-issue bound, not HBM bound (DESIGN.md)"}
+
+    # ---- e2e through the host-buffer C ABI: pinned host inputs -> host outputs, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        ctx = host.HostContext(local)
+        hbank = host.HostBank(bk["pathpt"], bk["segpt"], bk["hull"], bk["hull_cnt"], bk["obs"], bk["obs_cnt"], device=local)
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+        hout = dict(angle=pin([M], torch.float64), trans=pin([M, 2], torch.int32),
+                    segpt=pin([M, bank.nseg1, 2], torch.float64), pathpt=pin([M, bank.np, 2], torch.float64),
+                    obs=pin([M, O + bank.pomax, 3], torch.float64), obs_cnt=pin([M], torch.int32),
+                    rand_cnt=pin([M], torch.int32), bits=pin([M, R, (R + 31) // 32], torch.int32),
+                    tries=pin([M], torch.int32), valid=pin([M], torch.uint8), counters=np.zeros(4, dtype=np.uint64))
+        hv64, hv32, hvd = pin([n_seg], torch.uint8), pin([n_seg], torch.uint8), pin([n_seg], torch.uint8)
+        hgmm = pin([n_gmm, 2], torch.float32)
+        s64, s32 = segs64_h.numpy(), segs32_h.numpy()
+        gm, gs, gw = g_mean.cpu().numpy(), g_std.cpu().numpy(), g_w.cpu().numpy()
+
+        def e2e_step(it):
+            map0 = (it * world + rank) * M
+            host.generate_maps_host(ctx, hbank, map0, M, REPS, O, hout, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED,
+                                    raster_inflate=clear_px / 2)
+            ctx.segcheck_edage_f64(s64, hout["obs"], hout["obs_cnt"], clear_px, out=hv64)
+            ctx.segcheck_mpnet_f32(s32, hout["obs"], hout["obs_cnt"], clear_px, out=hv32)
+            ctx.dda_gridcheck(hout["bits"], R, s32, out=hvd)
+            ctx.gmm_sample(SEED, map0 * GMM_PER_MAP, n_gmm, gm, gs, gw, out=hgmm)
+
+        e2e_steps = max(2, min(args.steps, 5))
+        for it in range(2):
+            e2e_step(it)
+        b0 = ctx.bytes_moved()
+        barrier()
+        t0 = time.perf_counter()
+        for it in range(e2e_steps):
+            e2e_step(100 + it)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        b1 = ctx.bytes_moved()
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        # host results equal the device-resident ones for the same global map range?  (cheap spot check)
+        e2e = {"value": seg_per_step * e2e_steps / dt, "unit": "segments/s",
+               "h2d_bytes_per_step": (b1[0] - b0[0]) // e2e_steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // e2e_steps,
+               "ms_per_step": 1e3 * dt / e2e_steps, "valid_paths_per_s": M * world * e2e_steps / dt,
+               "timer": "host wall clock around synchronous host-API calls (each call synchronises before returning)"}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = cpu_baseline(args.cpu_sample_maps, os.cpu_count() or 1)
+
+    if rank == 0:
+        line = {"metric": "collision-checked segments/sec", "value": value, "unit": "segments/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32+u32", "data": "synthetic",
+                "valid_paths_per_s": valid_per_s,
+                "config": {"workload": "config2: %d maps/GPU/step, R=224, O=50 candidate circles, %d segments/map x "
+                                       "{A11 f64, A12 f32, DDA}, %d GMM samples/map, clearance 1 (4.48 px), bank of %d "
+                                       "target paths" % (M, SEGS_PER_MAP, GMM_PER_MAP, N_BANK),
+                           "maps_per_gpu": M, "segments_per_step": seg_per_step, "parallelism": "map-sharded x%d" % world,
+                           "l2": "inputs larger than L2 (segments 492 MB + labels 162 MB per step); no flush needed",
+                           "placement_tries_per_map": tries / max(maps_done, 1),
+                           "accepted_random_obstacles_per_map": acc_obs / max(maps_done, 1)},
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "counts_all_gathered": {"maps": maps_done, "valid_paths": valid,
+                                                          "accepted_obstacles": acc_obs, "placement_tries": tries}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--maps", type=int, default=10000, help="maps per GPU per step")
+    ap.add_argument("--cpu-sample-maps", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -192,6 +192,22 @@ int ppnet_clearance_filter_f64_host(void* ctx, const double* pathpt, int32_t np,
                                     int32_t O, int64_t n_maps, double map_size, double resolution,
                                     double clearance, uint8_t* accept, double* out, int32_t* out_cnt);
 
+/* Target-path bank resident on the device (host arrays in, opaque handle out).                    */
+int ppnet_bank_upload(int32_t device, const double* pathpt, const double* segpt, const double* hull,
+                      const int32_t* hull_cnt, const double* obs, const int32_t* obs_cnt,
+                      int32_t n_bank, int32_t np, int32_t nseg1, int32_t hmax, int32_t pomax,
+                      void** bank);
+int ppnet_bank_free(void* bank);
+/* MapGenerate.generate with HOST outputs: `params` carries the settings and host out_* pointers
+ * (its bank_* and in_* fields are ignored; counters, if set, is a host uint64[4] accumulator).    */
+int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* params);
+int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t resolution, int64_t n_maps,
+                             const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
+                             int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit);
+int ppnet_gmm_sample_host(void* ctx, uint64_t seed, uint64_t sample0, int64_t n, int32_t order,
+                          int32_t dim, const float* mean, const float* stdv, const float* weights,
+                          float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,8 +11,11 @@
 //      `while` of the reference).  In parity mode the draws come from the caller instead.
 //   2. all threads rotate/translate the 1000 path points + 11 segment points (label, 16.2 KB -- the
 //      dominant HBM stream, written with 16-byte stores) and keep the odd-indexed points in shared memory.
-//   3. each warp owns candidate circles round-robin: min squared distance to the staged odd points,
-//      one sqrt, the reference's `min(dis) > r_px + c*R/M` verdict; ordered compaction by ballot scan.
+//   3. candidate circles: thread k draws candidate k once; each warp then owns candidates round-robin.  The
+//      staged odd points are grouped into boxes of 16 consecutive points; a lane owns a box, skips it when the
+//      candidate is farther from the box than the threshold plus a 1e7-ulp margin (those points cannot be the
+//      ones that decide `min(dis) > r_px + c*R/M`), otherwise evaluates its points with the reference's exact
+//      un-fused arithmetic.  One sqrt per candidate; ordered compaction by ballot scan.
 //   4. the path-hugging obstacles of the target path are placed with the same rigid transform and appended.
 //   5. optional: all obstacles rasterised into a shared-memory bitmap and streamed out.
 // The target-path bank (16 KB / path) is read through L2; nothing else is read from HBM.
@@ -25,6 +28,7 @@ namespace ppnet {
 
 constexpr int kGenThreads = 256;
 constexpr int kGenWarps = kGenThreads / 32;
+constexpr int kBlkPts = 16;
 
 // Path.coord_rotation (Path.py:271-274) = np.dot(2x2, 2xN): OpenBLAS dgemm accumulates with FMA on
 // AVX2/AVX-512 hosts: out = fma(r01, x1, r00 * x0).   (waypoint parity is 1e-5; verdict parity of
@@ -111,9 +115,11 @@ generate_kernel(ppnet_gen_params P) {
     const int omax_out = O + P.pomax;
     int W = 0, words = 0;
     if (P.out_bits) { W = ((int)P.resolution + 31) / 32; words = (int)P.resolution * W; }
+    const int n_blk = (n_odd + kBlkPts - 1) / kBlkPts;       // boxes of kBlkPts consecutive odd points
     double2* odd = reinterpret_cast<double2*>(smem_raw);
     double2* hull = odd + n_odd;
-    uint32_t* bm = reinterpret_cast<uint32_t*>(hull + P.hmax);
+    double4* box = reinterpret_cast<double4*>(hull + P.hmax + (P.hmax & 1));    // (row_lo, row_hi, col_lo, col_hi), 32-B aligned
+    uint32_t* bm = reinterpret_cast<uint32_t*>(box + n_blk);
     double* sobs = reinterpret_cast<double*>(bm + ((words + 3) & ~3));
     uint8_t* acc_s = reinterpret_cast<uint8_t*>(sobs + 3 * omax_out);
     __shared__ GenShared sh;
@@ -219,7 +225,16 @@ generate_kernel(ppnet_gen_params P) {
     // ---- 3. candidate circles: draws + clearance verdict (MapGenerate.py:128-143) ----------------------
     const double M = P.map_size;
     const double thr_c = __dmul_rn(__ddiv_rn(P.clearance, M), R);             // c / M * R
-    for (int k = warp; k < O; k += kGenWarps) {
+    for (int b = threadIdx.x; b < n_blk; b += kGenThreads) {                  // boxes of the staged odd points
+        double4 bb = make_double4(CUDART_INF, -CUDART_INF, CUDART_INF, -CUDART_INF);
+        const int e = min(n_odd, (b + 1) * kBlkPts);
+        for (int i = b * kBlkPts; i < e; ++i) {
+            const double2 p = odd[i];
+            bb.x = fmin(bb.x, p.x); bb.y = fmax(bb.y, p.x); bb.z = fmin(bb.z, p.y); bb.w = fmax(bb.w, p.y);
+        }
+        box[b] = bb;
+    }
+    for (int k = threadIdx.x; k < O; k += kGenThreads) {                      // one Philox draw per candidate
         double x, y, r;
         if (P.in_cand) {
             const double* c = P.in_cand + ((size_t)lm * O + k) * 3;
@@ -227,15 +242,35 @@ generate_kernel(ppnet_gen_params P) {
         } else {
             draw_candidate(key, g, k, O, M, P.obstacle_size, x, y, r);
         }
-        const double q0 = __dmul_rn(__ddiv_rn(x, M), R), q1 = __dmul_rn(__ddiv_rn(y, M), R);
-        const double rimg = __dmul_rn(__ddiv_rn(r, M), R);
-        const double m2 = warp_min_d2_gen(odd, n_odd, q0, q1);
-        const bool ok = __dsqrt_rn(m2) > __dadd_rn(rimg, thr_c);
-        if (lane == 0) {
-            acc_s[k] = ok ? 1 : 0;
-            double* o = sobs + 3 * k;                      // [coord_img[1], coord_img[0], radius_img]  (:143)
-            o[0] = q1; o[1] = q0; o[2] = rimg;
+        double* o = sobs + 3 * k;                          // [coord_img[1], coord_img[0], radius_img]  (:134-136, :143)
+        o[0] = __dmul_rn(__ddiv_rn(y, M), R);
+        o[1] = __dmul_rn(__ddiv_rn(x, M), R);
+        o[2] = __dmul_rn(__ddiv_rn(r, M), R);
+    }
+    __syncthreads();
+    for (int k = warp; k < O; k += kGenWarps) {
+        const double q1 = sobs[3 * k], q0 = sobs[3 * k + 1], rimg = sobs[3 * k + 2];
+        const double thr = __dadd_rn(rimg, thr_c);
+        // squared cull radius: (thr + margin)^2 with the margin ~1e7 ulp of the coordinates involved
+        const double cr = thr + 1e-9 * (R + fabs(q0) + fabs(q1) + fabs(thr));
+        const double cull2 = cr * cr * (1.0 + 1e-12);
+        double m2 = CUDART_INF;
+        for (int b = lane; b < n_blk; b += 32) {
+            const double4 bb = box[b];
+            const double ex = fmax(fmax(bb.x - q0, q0 - bb.y), 0.0), ey = fmax(fmax(bb.z - q1, q1 - bb.w), 0.0);
+            if (ex * ex + ey * ey > cull2) continue;       // NaN never culls
+            const int e = min(n_odd, (b + 1) * kBlkPts);
+            for (int i = b * kBlkPts; i < e; ++i) {
+                const double2 p = odd[i];
+                const double ax = __dsub_rn(p.x, q0), ay = __dsub_rn(p.y, q1);     // scipy euclidean: un-fused
+                m2 = fmin(m2, __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+            }
         }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, sft));
+        // sqrt is monotone: sqrt(min d^2) == min sqrt(d^2); skipped boxes only hold points with d > thr
+        const bool ok = __dsqrt_rn(m2) > thr;                                     // :142
+        if (lane == 0) acc_s[k] = ok ? 1 : 0;
     }
     __syncthreads();
     // ordered compaction of the accepted candidates (the reference appends in loop order)
@@ -338,8 +373,8 @@ extern "C" int ppnet_generate_maps(const ppnet_gen_params* p, void* stream) {
                   "generate_maps: resolution must be a positive integer");
     PPNET_REQUIRE((p->in_angle == nullptr) == (p->in_trans == nullptr), "generate_maps: in_angle and in_trans go together");
     const int R = (int)p->resolution, W = (R + 31) / 32;
-    size_t smem = sizeof(double2) * (size_t)(p->np / 2 + p->hmax) + sizeof(double) * 3 * (size_t)(p->obstacles_num + p->pomax) +
-                  (size_t)p->obstacles_num + 32;
+    size_t smem = sizeof(double2) * (size_t)(p->np / 2 + p->hmax + 1) + 32 * (size_t)((p->np / 2 + kBlkPts - 1) / kBlkPts) +
+                  sizeof(double) * 3 * (size_t)(p->obstacles_num + p->pomax) + (size_t)p->obstacles_num + 64;
     if (p->out_bits) smem += (size_t)(((R * W) + 3) & ~3) * 4;
     PPNET_REQUIRE(smem <= 220 * 1024, "generate_maps: shared memory budget exceeded (%zu bytes)", smem);
     if (smem > 48 * 1024)

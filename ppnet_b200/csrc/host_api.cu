@@ -212,3 +212,212 @@ extern "C" int ppnet_clearance_filter_f64_host(void* ctx, const double* pathpt, 
     PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
     return PPNET_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// generate / dda / gmm with host buffers
+// ------------------------------------------------------------------------------------------------
+namespace ppnet {
+struct Bank {          // device copy of a target-path bank, owned by the context user
+    int device = 0;
+    double *pathpt = nullptr, *segpt = nullptr, *hull = nullptr, *obs = nullptr;
+    int32_t *hull_cnt = nullptr, *obs_cnt = nullptr;
+    int32_t n_bank = 0, np = 0, nseg1 = 0, hmax = 0, pomax = 0;
+};
+template <typename T>
+static int upload(T** dst, const T* src, size_t n) {
+    *dst = nullptr;
+    if (n == 0) return PPNET_OK;
+    if (cudaMalloc((void**)dst, n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); set_error("bank: cudaMalloc failed"); return PPNET_E_NOMEM; }
+    PPNET_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return PPNET_OK;
+}
+}  // namespace ppnet
+
+extern "C" int ppnet_bank_upload(int32_t device, const double* pathpt, const double* segpt, const double* hull,
+                                 const int32_t* hull_cnt, const double* obs, const int32_t* obs_cnt, int32_t n_bank,
+                                 int32_t np, int32_t nseg1, int32_t hmax, int32_t pomax, void** bank) {
+    PPNET_REQUIRE(bank && pathpt && hull && hull_cnt, "bank_upload: null pointer");
+    PPNET_REQUIRE(n_bank > 0 && np >= 0 && nseg1 >= 0 && hmax > 0 && pomax >= 0, "bank_upload: bad sizes");
+    PPNET_REQUIRE(pomax == 0 || (obs && obs_cnt), "bank_upload: obs is null");
+    PPNET_CUDA(cudaSetDevice(device));
+    Bank* b = new Bank();
+    b->device = device; b->n_bank = n_bank; b->np = np; b->nseg1 = nseg1; b->hmax = hmax; b->pomax = pomax;
+    int rc;
+    if ((rc = upload(&b->pathpt, pathpt, (size_t)n_bank * np * 2)) != PPNET_OK) return rc;
+    if ((rc = upload(&b->segpt, segpt, segpt ? (size_t)n_bank * nseg1 * 2 : 0)) != PPNET_OK) return rc;
+    if ((rc = upload(&b->hull, hull, (size_t)n_bank * hmax * 2)) != PPNET_OK) return rc;
+    if ((rc = upload(&b->hull_cnt, hull_cnt, (size_t)n_bank)) != PPNET_OK) return rc;
+    if ((rc = upload(&b->obs, obs, (size_t)n_bank * pomax * 3)) != PPNET_OK) return rc;
+    if ((rc = upload(&b->obs_cnt, obs_cnt, pomax ? (size_t)n_bank : 0)) != PPNET_OK) return rc;
+    *bank = b;
+    return PPNET_OK;
+}
+
+extern "C" int ppnet_bank_free(void* bank) {
+    Bank* b = (Bank*)bank;
+    if (!b) return PPNET_OK;
+    cudaSetDevice(b->device);
+    cudaFree(b->pathpt); cudaFree(b->segpt); cudaFree(b->hull); cudaFree(b->hull_cnt); cudaFree(b->obs); cudaFree(b->obs_cnt);
+    delete b;
+    return PPNET_OK;
+}
+
+// `p` carries the generation settings and HOST output pointers (bank_* / in_* fields are ignored: the bank
+// comes from `bank`, draws from Philox).  Maps are produced in slices; slice k's device->host copies overlap
+// slice k+1's kernel.
+extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* p) {
+    Ctx* c = (Ctx*)ctx;
+    Bank* b = (Bank*)bank;
+    PPNET_REQUIRE(c && b && p, "generate_maps_host: null argument");
+    PPNET_REQUIRE(p->n_maps >= 0, "generate_maps_host: negative n_maps");
+    PPNET_REQUIRE(!p->in_angle && !p->in_trans && !p->in_cand, "generate_maps_host: caller-supplied draws need the device API");
+    PPNET_CUDA(cudaSetDevice(c->device));
+    const int R = (int)p->resolution, W = (R + 31) / 32;
+    const int64_t O = p->obstacles_num, oo = O + b->pomax;
+    const int64_t kSlice = 2048;
+    // per-map byte sizes of the outputs, slot buffer ids: 0 pathpt, 1 segpt, 2 obs, 3 bits, 4 small ints, 5 counters
+    const size_t b_pp = sizeof(double) * 2 * (size_t)b->np, b_sp = sizeof(double) * 2 * (size_t)b->nseg1;
+    const size_t b_ob = sizeof(double) * 3 * (size_t)oo, b_bt = (size_t)R * W * 4;
+    const size_t b_small = 8 /*angle*/ + 8 /*trans*/ + 4 * 3 /*obs_cnt, rand_cnt, tries*/ + 4 /*valid, padded*/;
+    const int64_t n_slices = (p->n_maps + kSlice - 1) / kSlice;
+    std::vector<unsigned long long> cnt_keep(4 * (size_t)std::max<int64_t>(n_slices, 1), 0ull);
+    int k = 0;
+    for (int64_t m0 = 0; m0 < p->n_maps; m0 += kSlice, ++k) {
+        Slot& s = c->slot[k & 1];
+        const int64_t nm = std::min(kSlice, p->n_maps - m0);
+        int rc;
+        if ((rc = slot_reserve(s, 0, b_pp * nm)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 1, b_sp * nm + 16)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 2, b_ob * nm + 16)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 3, b_bt * nm + 16)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 4, b_small * nm + 64)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 5, 64)) != PPNET_OK) return rc;
+        char* small = (char*)s.buf[4];
+        double* d_angle = (double*)small;
+        int32_t* d_trans = (int32_t*)(small + 8 * nm);
+        int32_t* d_ocnt = (int32_t*)(small + 16 * nm);
+        int32_t* d_rcnt = (int32_t*)(small + 20 * nm);
+        int32_t* d_tries = (int32_t*)(small + 24 * nm);
+        uint8_t* d_valid = (uint8_t*)(small + 28 * nm);
+        PPNET_CUDA(cudaMemsetAsync(s.buf[5], 0, 32, s.st));
+        ppnet_gen_params q = *p;
+        q.bank_pathpt = b->pathpt; q.bank_segpt = b->segpt; q.bank_hull = b->hull; q.bank_hull_cnt = b->hull_cnt;
+        q.bank_obs = b->obs; q.bank_obs_cnt = b->obs_cnt;
+        q.n_bank = b->n_bank; q.np = b->np; q.nseg1 = b->nseg1; q.hmax = b->hmax; q.pomax = b->pomax;
+        q.map0 = p->map0 + m0; q.n_maps = nm;
+        q.out_pathpt = p->out_pathpt ? (double*)s.buf[0] : nullptr;
+        q.out_segpt = p->out_segpt ? (double*)s.buf[1] : nullptr;
+        q.out_obs = (double*)s.buf[2];
+        q.out_bits = p->out_bits ? (uint32_t*)s.buf[3] : nullptr;
+        q.out_angle = d_angle; q.out_trans = d_trans; q.out_obs_cnt = d_ocnt; q.out_rand_cnt = d_rcnt;
+        q.out_tries = d_tries; q.out_valid = d_valid;
+        q.counters = (unsigned long long*)s.buf[5];
+        if ((rc = ppnet_generate_maps(&q, (void*)s.st)) != PPNET_OK) return rc;
+#define PPNET_D2H(host, devp, bytes)                                                                        \
+    if (host) {                                                                                             \
+        PPNET_CUDA(cudaMemcpyAsync((char*)(host), devp, (bytes), cudaMemcpyDeviceToHost, s.st));            \
+        c->d2h_bytes += (int64_t)(bytes);                                                                   \
+    }
+        PPNET_D2H(p->out_pathpt ? (char*)p->out_pathpt + b_pp * m0 : nullptr, s.buf[0], b_pp * nm);
+        PPNET_D2H(p->out_segpt ? (char*)p->out_segpt + b_sp * m0 : nullptr, s.buf[1], b_sp * nm);
+        PPNET_D2H(p->out_obs ? (char*)p->out_obs + b_ob * m0 : nullptr, s.buf[2], b_ob * nm);
+        PPNET_D2H(p->out_bits ? (char*)p->out_bits + b_bt * m0 : nullptr, s.buf[3], b_bt * nm);
+        PPNET_D2H(p->out_angle ? p->out_angle + m0 : nullptr, d_angle, 8 * (size_t)nm);
+        PPNET_D2H(p->out_trans ? p->out_trans + 2 * m0 : nullptr, d_trans, 8 * (size_t)nm);
+        PPNET_D2H(p->out_obs_cnt ? p->out_obs_cnt + m0 : nullptr, d_ocnt, 4 * (size_t)nm);
+        PPNET_D2H(p->out_rand_cnt ? p->out_rand_cnt + m0 : nullptr, d_rcnt, 4 * (size_t)nm);
+        PPNET_D2H(p->out_tries ? p->out_tries + m0 : nullptr, d_tries, 4 * (size_t)nm);
+        PPNET_D2H(p->out_valid ? p->out_valid + m0 : nullptr, d_valid, (size_t)nm);
+        if (p->counters)
+            PPNET_CUDA(cudaMemcpyAsync(cnt_keep.data() + 4 * k, s.buf[5], 32, cudaMemcpyDeviceToHost, s.st));
+    }
+    PPNET_CUDA(cudaStreamSynchronize(c->slot[0].st));
+    PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
+    if (p->counters)
+        for (int64_t q = 0; q < n_slices; ++q)
+            for (int i = 0; i < 4; ++i) p->counters[i] += cnt_keep[4 * q + i];
+    return PPNET_OK;
+}
+
+extern "C" int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t resolution, int64_t n_maps,
+                                        const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
+                                        int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit) {
+    Ctx* c = (Ctx*)ctx;
+    PPNET_REQUIRE(c, "dda_host: null context");
+    PPNET_REQUIRE(n_maps >= 0 && n_segs >= 0 && resolution > 0, "dda_host: bad sizes");
+    if (n_maps == 0 || n_segs == 0) return PPNET_OK;
+    PPNET_REQUIRE(bits && segs_xy && verdict, "dda_host: null pointer");
+    PPNET_REQUIRE(seg_off || segs_per_map * n_maps == n_segs, "dda_host: bad uniform grouping");
+    PPNET_CUDA(cudaSetDevice(c->device));
+    const int W = (resolution + 31) / 32;
+    const size_t bm = (size_t)resolution * W * 4;
+    std::vector<Slice> sl = make_slices(n_segs, seg_off, segs_per_map, n_maps, 1 << 20);
+    std::vector<std::vector<int64_t>> rel_keep(sl.size());
+    for (size_t k = 0; k < sl.size(); ++k) {
+        Slot& s = c->slot[k & 1];
+        const Slice& q = sl[k];
+        const int64_t ns = q.s1 - q.s0, nm = q.m1 - q.m0;
+        int rc;
+        if ((rc = slot_reserve(s, 0, 16 * (size_t)ns)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 1, bm * nm)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 3, (size_t)ns)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 4, 4 * (size_t)ns)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 5, 8 * (size_t)(nm + 1))) != PPNET_OK) return rc;
+        PPNET_CUDA(cudaMemcpyAsync(s.buf[0], segs_xy + 4 * q.s0, 16 * (size_t)ns, cudaMemcpyHostToDevice, s.st));
+        PPNET_CUDA(cudaMemcpyAsync(s.buf[1], (const char*)bits + bm * q.m0, bm * nm, cudaMemcpyHostToDevice, s.st));
+        c->h2d_bytes += (int64_t)(16 * ns + bm * nm);
+        const int64_t* d_off = nullptr;
+        int64_t spm = segs_per_map;
+        if (seg_off) {
+            rel_keep[k].resize(nm + 1);
+            int64_t longest = 1;
+            for (int64_t i = 0; i <= nm; ++i) rel_keep[k][i] = seg_off[q.m0 + i] - q.s0;
+            for (int64_t i = 0; i < nm; ++i) longest = std::max(longest, rel_keep[k][i + 1] - rel_keep[k][i]);
+            PPNET_CUDA(cudaMemcpyAsync(s.buf[5], rel_keep[k].data(), 8 * (size_t)(nm + 1), cudaMemcpyHostToDevice, s.st));
+            d_off = (const int64_t*)s.buf[5];
+            spm = longest;
+        }
+        rc = ppnet_dda_gridcheck((const uint32_t*)s.buf[1], resolution, nm, (const float*)s.buf[0], ns, d_off, spm,
+                                 (uint8_t*)s.buf[3], first_hit ? (int32_t*)s.buf[4] : nullptr, (void*)s.st);
+        if (rc != PPNET_OK) return rc;
+        PPNET_CUDA(cudaMemcpyAsync(verdict + q.s0, s.buf[3], (size_t)ns, cudaMemcpyDeviceToHost, s.st));
+        if (first_hit) PPNET_CUDA(cudaMemcpyAsync(first_hit + q.s0, s.buf[4], 4 * (size_t)ns, cudaMemcpyDeviceToHost, s.st));
+        c->d2h_bytes += ns + (first_hit ? 4 * ns : 0);
+    }
+    PPNET_CUDA(cudaStreamSynchronize(c->slot[0].st));
+    PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
+    return PPNET_OK;
+}
+
+extern "C" int ppnet_gmm_sample_host(void* ctx, uint64_t seed, uint64_t sample0, int64_t n, int32_t order, int32_t dim,
+                                     const float* mean, const float* stdv, const float* weights, float* out) {
+    Ctx* c = (Ctx*)ctx;
+    PPNET_REQUIRE(c && mean && stdv && weights && (out || n == 0), "gmm_sample_host: null argument");
+    PPNET_REQUIRE(n >= 0 && order > 0 && dim > 0, "gmm_sample_host: bad sizes");
+    if (n == 0) return PPNET_OK;
+    PPNET_CUDA(cudaSetDevice(c->device));
+    const int64_t kSlice = 1 << 21;
+    int k = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += kSlice, ++k) {
+        Slot& s = c->slot[k & 1];
+        const int64_t ni = std::min(kSlice, n - i0);
+        int rc;
+        if ((rc = slot_reserve(s, 0, 4 * (size_t)ni * dim)) != PPNET_OK) return rc;
+        if ((rc = slot_reserve(s, 1, 4 * (size_t)order * (2 * dim + 1) + 64)) != PPNET_OK) return rc;
+        float* d_mean = (float*)s.buf[1];
+        float* d_std = d_mean + order * dim;
+        float* d_w = d_std + order * dim;
+        PPNET_CUDA(cudaMemcpyAsync(d_mean, mean, 4 * (size_t)order * dim, cudaMemcpyHostToDevice, s.st));
+        PPNET_CUDA(cudaMemcpyAsync(d_std, stdv, 4 * (size_t)order * dim, cudaMemcpyHostToDevice, s.st));
+        PPNET_CUDA(cudaMemcpyAsync(d_w, weights, 4 * (size_t)order, cudaMemcpyHostToDevice, s.st));
+        c->h2d_bytes += 4 * order * (2 * dim + 1);
+        rc = ppnet_gmm_sample(seed, sample0 + (uint64_t)i0, ni, order, dim, d_mean, d_std, d_w, (float*)s.buf[0], nullptr,
+                              (void*)s.st);
+        if (rc != PPNET_OK) return rc;
+        PPNET_CUDA(cudaMemcpyAsync(out + i0 * dim, s.buf[0], 4 * (size_t)ni * dim, cudaMemcpyDeviceToHost, s.st));
+        c->d2h_bytes += 4 * ni * dim;
+    }
+    PPNET_CUDA(cudaStreamSynchronize(c->slot[0].st));
+    PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
+    return PPNET_OK;
+}

@@ -132,8 +132,33 @@ __device__ __forceinline__ Circle<T> make_circle(const double* __restrict__ o, d
 
 constexpr int kCircTile = 128;       // circles staged per pass
 constexpr int kSegThreads = 256;
-constexpr int kSegPerThread = 2;     // two segments in flight per thread (ILP across the LDS latency)
-constexpr int kSegChunk = kSegThreads * kSegPerThread;
+template <typename T> struct SegCfg;      // segments per thread: registers (f64) vs ILP (f32)
+template <> struct SegCfg<double> { static constexpr int kPerThread = 1; };
+template <> struct SegCfg<float> { static constexpr int kPerThread = 2; };
+
+// ---- exact-safe spatial culling -------------------------------------------------------------------------
+// A circle can only collide with a segment whose bounding box meets the circle's box inflated by thr:
+//   vertex test  |e - o| < thr            => o is within thr of the endpoint e,
+//   edge test    |dis| < thr and the foot of the perpendicular strictly between s and e
+//                                         => o is within thr of a point of the segment.
+// Both boxes are further inflated by a margin thousands of ulps wide (kCull * magnitude), so a pair that the
+// grid separates is separated by far more than any rounding of the reference's operation sequence could
+// bridge (for the edge test the foot then lies beyond an end by >= the margin, where normalised
+// (p-s).(p-e) is within 1e-6 of +1).  Culled pairs are exactly the pairs whose verdict is "no".
+// The staged circles are binned into an 8x8 grid over [0, bound]^2 (cell lists in shared memory); a segment
+// only walks the lists of the cells its box touches.  The bin function is monotone, so two intersecting
+// intervals always share a bin.  Long segments (box > kMaxQueryCells bins) and non-finite coordinates take
+// the plain loop over all staged circles.
+constexpr int kGridN = 8;
+constexpr int kGridCells = kGridN * kGridN;
+constexpr int kMaxQueryCells = 12;
+template <typename T> struct Cull;
+template <> struct Cull<double> { static constexpr double k = 1e-9; };
+template <> struct Cull<float> { static constexpr float k = 1e-3f; };
+
+__device__ __forceinline__ int bin_of(float v, float scale) {          // monotone non-decreasing in v
+    return (int)fminf(fmaxf(v * scale, 0.0f), (float)(kGridN - 1));
+}
 
 template <typename T> struct Vec4;   // 4 coordinates of one segment
 template <> struct Vec4<double> {
@@ -156,6 +181,8 @@ __global__ void __launch_bounds__(kSegThreads)
 segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, int64_t segs_per_map,
                 const double* __restrict__ obs, const int32_t* __restrict__ obs_cnt, int omax,
                 double clearance, T bound, uint8_t* __restrict__ verdict, uint8_t* __restrict__ steer) {
+    constexpr int kSegPerThread = SegCfg<T>::kPerThread;
+    constexpr int kSegChunk = kSegThreads * kSegPerThread;
     const int m = blockIdx.x;
     const int64_t lo = seg_off ? seg_off[m] : (int64_t)m * segs_per_map;
     const int64_t hi = seg_off ? seg_off[m + 1] : lo + segs_per_map;
@@ -163,7 +190,11 @@ segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, 
     if (base >= hi) return;                       // whole CTA exits together
 
     __shared__ Circle<T> sc[kCircTile];
+    __shared__ uint8_t cell_idx[kGridCells][kCircTile];
+    __shared__ int cell_cnt[kGridCells];
     const int cnt = min(obs_cnt[m], omax);
+    const bool use_grid = bound > T(0) && bound < T(1e30);
+    const float bscale = use_grid ? (float)kGridN / (float)bound : 0.0f;
     const double* __restrict__ mobs = obs + (size_t)m * omax * 3;
 
     SegState<T> g[kSegPerThread];
@@ -184,14 +215,53 @@ segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, 
     for (int t0 = 0; t0 < cnt; t0 += kCircTile) {
         const int nt = min(kCircTile, cnt - t0);
         __syncthreads();
-        if (threadIdx.x < nt) sc[threadIdx.x] = make_circle<T>(mobs + 3 * (t0 + threadIdx.x), clearance);
+        if (threadIdx.x < kGridCells) cell_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        if (threadIdx.x < nt) {
+            const Circle<T> c = make_circle<T>(mobs + 3 * (t0 + threadIdx.x), clearance);
+            sc[threadIdx.x] = c;
+            // circles that can never answer "hit" (thr <= 0 or NaN, non-finite centre) are not binned at all
+            if (use_grid && c.thr > T(0) && FP<T>::abs_(c.ox) < T(1e30) && FP<T>::abs_(c.oy) < T(1e30)) {
+                const T h = c.thr + Cull<T>::k * (FP<T>::abs_(c.ox) + FP<T>::abs_(c.oy) + c.thr + bound);
+                const int x0 = bin_of((float)(c.ox - h), bscale), x1 = bin_of((float)(c.ox + h), bscale);
+                const int y0 = bin_of((float)(c.oy - h), bscale), y1 = bin_of((float)(c.oy + h), bscale);
+                for (int by = y0; by <= y1; ++by)
+                    for (int bx = x0; bx <= x1; ++bx) {
+                        const int cell = by * kGridN + bx;
+                        cell_idx[cell][atomicAdd(&cell_cnt[cell], 1)] = (uint8_t)threadIdx.x;
+                    }
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kSegPerThread; ++k) {
             if (!live[k] || hit[k]) continue;
-            for (int j = 0; j < nt; ++j) {
-                if (pair_hit<T, MODE>(g[k], sc[j])) { hit[k] = true; break; }
+            const SegState<T>& q = g[k];
+            bool brute = !use_grid;
+            int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+            if (!brute) {
+                const T ms = Cull<T>::k * (q.mag + bound);
+                const T lox = (q.s0 < q.e0 ? q.s0 : q.e0) - ms, hix = (q.s0 < q.e0 ? q.e0 : q.s0) + ms;
+                const T loy = (q.s1 < q.e1 ? q.s1 : q.e1) - ms, hiy = (q.s1 < q.e1 ? q.e1 : q.s1) + ms;
+                // NaN / inf coordinates fail this test and take the plain loop
+                if (!(FP<T>::abs_(lox) < T(1e30) && FP<T>::abs_(hix) < T(1e30) && FP<T>::abs_(loy) < T(1e30) &&
+                      FP<T>::abs_(hiy) < T(1e30))) brute = true;
+                else {
+                    x0 = bin_of((float)lox, bscale); x1 = bin_of((float)hix, bscale);
+                    y0 = bin_of((float)loy, bscale); y1 = bin_of((float)hiy, bscale);
+                    if ((x1 - x0 + 1) * (y1 - y0 + 1) > kMaxQueryCells) brute = true;
+                }
             }
+            if (brute) { x0 = x1 = y0 = y1 = 0; }                  // one pseudo-bin holding every staged circle
+            for (int by = y0; by <= y1 && !hit[k]; ++by)
+                for (int bx = x0; bx <= x1 && !hit[k]; ++bx) {
+                    const int cell = by * kGridN + bx;
+                    const int nc = brute ? nt : cell_cnt[cell];
+                    for (int t = 0; t < nc; ++t) {
+                        const int j = brute ? t : (int)cell_idx[cell][t];
+                        if (pair_hit<T, MODE>(q, sc[j])) { hit[k] = true; break; }
+                    }
+                }
         }
     }
 
@@ -236,6 +306,7 @@ static int launch(const T* pts, int64_t n_segs, const int64_t* seg_off, int64_t 
     int64_t dummy = 1;
     int rc = check_common(pts, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, &dummy);
     if (rc != PPNET_OK || dummy == 0) return rc;
+    constexpr int kSegChunk = kSegThreads * SegCfg<T>::kPerThread;
     const int64_t per_map = segs_per_map > 0 ? segs_per_map : n_segs;
     const int64_t chunks = (per_map + kSegChunk - 1) / kSegChunk;
     PPNET_REQUIRE(chunks <= 65535, "segcheck: more than 65535*512 segments in one map");

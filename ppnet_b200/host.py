@@ -1,0 +1,161 @@
+"""Host-buffer boundary: numpy arrays (pageable or pinned) in, numpy arrays out, through the `*_host` entry
+points of the C ABI.  This is the call a user of the reference makes -- host data in, host data out; the
+copies and the kernels are inside.  No CPU fallback."""
+import ctypes
+
+import numpy as np
+
+from ._lib import PPNetError, check, lib
+from .ops import DEFAULT_BOUND, DEFAULT_SEED, DOT_FUSED_SKX, GenParams
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+
+
+def _c(a, dt, name):
+    a = np.asarray(a)
+    if a.dtype != dt or not a.flags.c_contiguous:
+        raise PPNetError("%s must be a C-contiguous %s array" % (name, np.dtype(dt)))
+    return a
+
+
+class HostContext:
+    """Two CUDA streams + a grow-only device arena (ppnet_ctx_create)."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        check(lib().ppnet_ctx_create(ctypes.c_int32(device), ctypes.byref(self._h)), "ppnet_ctx_create")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().ppnet_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bytes_moved(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        check(lib().ppnet_ctx_bytes(self._h, ctypes.byref(a), ctypes.byref(b)), "ppnet_ctx_bytes")
+        return a.value, b.value
+
+    # ---- A11
+    def segcheck_edage_f64(self, pts_rc, obs, obs_cnt, clearance, seg_off=None, bound=DEFAULT_BOUND,
+                           dot_mode=DOT_FUSED_SKX, out=None):
+        pts = _c(pts_rc, np.float64, "pts_rc").reshape(-1, 4)
+        ob, oc = _c(obs, np.float64, "obs"), _c(obs_cnt, np.int32, "obs_cnt")
+        n, m = len(pts), len(oc)
+        so = _c(seg_off, np.int64, "seg_off") if seg_off is not None else None
+        out = np.empty(n, dtype=np.uint8) if out is None else out
+        check(lib().ppnet_segcheck_edage_f64_host(self._h, _p(pts), ctypes.c_int64(n), _p(so),
+                                                  ctypes.c_int64(0 if so is not None else n // max(m, 1)),
+                                                  ctypes.c_int64(m), _p(ob), _p(oc), ctypes.c_int32(ob.shape[1]),
+                                                  ctypes.c_double(clearance), ctypes.c_double(bound),
+                                                  ctypes.c_int32(dot_mode), _p(out)), "ppnet_segcheck_edage_f64_host")
+        return out
+
+    # ---- A12
+    def segcheck_mpnet_f32(self, pts_xy, obs, obs_cnt, clearance, seg_off=None, bound=DEFAULT_BOUND, out=None,
+                           steer=None):
+        pts = _c(pts_xy, np.float32, "pts_xy").reshape(-1, 4)
+        ob, oc = _c(obs, np.float64, "obs"), _c(obs_cnt, np.int32, "obs_cnt")
+        n, m = len(pts), len(oc)
+        so = _c(seg_off, np.int64, "seg_off") if seg_off is not None else None
+        out = np.empty(n, dtype=np.uint8) if out is None else out
+        check(lib().ppnet_segcheck_mpnet_f32_host(self._h, _p(pts), ctypes.c_int64(n), _p(so),
+                                                  ctypes.c_int64(0 if so is not None else n // max(m, 1)),
+                                                  ctypes.c_int64(m), _p(ob), _p(oc), ctypes.c_int32(ob.shape[1]),
+                                                  ctypes.c_double(clearance), ctypes.c_double(bound), _p(out),
+                                                  _p(steer)), "ppnet_segcheck_mpnet_f32_host")
+        return out
+
+    # ---- A14
+    def clearance_filter_f64(self, pathpt, cand, map_size, resolution, clearance):
+        pp, cd = _c(pathpt, np.float64, "pathpt"), _c(cand, np.float64, "cand")
+        m, np_, _ = pp.shape
+        O = cd.shape[1]
+        acc = np.empty([m, O], dtype=np.uint8)
+        out = np.zeros([m, O, 3], dtype=np.float64)
+        cnt = np.empty(m, dtype=np.int32)
+        check(lib().ppnet_clearance_filter_f64_host(self._h, _p(pp), ctypes.c_int32(np_), _p(cd), ctypes.c_int32(O),
+                                                    ctypes.c_int64(m), ctypes.c_double(map_size),
+                                                    ctypes.c_double(resolution), ctypes.c_double(clearance), _p(acc),
+                                                    _p(out), _p(cnt)), "ppnet_clearance_filter_f64_host")
+        return acc, out, cnt
+
+    # ---- DDA
+    def dda_gridcheck(self, bits, resolution, segs_xy, seg_off=None, out=None, first_hit=None):
+        b = np.asarray(bits)
+        if b.dtype not in (np.uint32, np.int32) or not b.flags.c_contiguous:
+            raise PPNetError("bits must be a C-contiguous uint32 array")
+        sg = _c(segs_xy, np.float32, "segs_xy").reshape(-1, 4)
+        so = _c(seg_off, np.int64, "seg_off") if seg_off is not None else None
+        n, m = len(sg), b.shape[0]
+        out = np.empty(n, dtype=np.uint8) if out is None else out
+        check(lib().ppnet_dda_gridcheck_host(self._h, _p(b), ctypes.c_int32(resolution), ctypes.c_int64(m), _p(sg),
+                                             ctypes.c_int64(n), _p(so),
+                                             ctypes.c_int64(0 if so is not None else n // max(m, 1)), _p(out),
+                                             _p(first_hit)), "ppnet_dda_gridcheck_host")
+        return out
+
+    # ---- GMM
+    def gmm_sample(self, seed, sample0, n, mean, std, weights, out=None):
+        mean, std, w = _c(mean, np.float32, "mean"), _c(std, np.float32, "std"), _c(weights, np.float32, "weights")
+        k, d = mean.shape
+        out = np.empty([n, d], dtype=np.float32) if out is None else out
+        check(lib().ppnet_gmm_sample_host(self._h, ctypes.c_uint64(seed), ctypes.c_uint64(sample0), ctypes.c_int64(n),
+                                          ctypes.c_int32(k), ctypes.c_int32(d), _p(mean), _p(std), _p(w), _p(out)),
+              "ppnet_gmm_sample_host")
+        return out
+
+
+class HostBank:
+    """Device copy of a target-path bank built from host arrays (ppnet_bank_upload)."""
+
+    def __init__(self, pathpt, segpt, hull, hull_cnt, obs=None, obs_cnt=None, device=0):
+        pp, sp = _c(pathpt, np.float64, "pathpt"), _c(segpt, np.float64, "segpt")
+        hl, hc = _c(hull, np.float64, "hull"), _c(hull_cnt, np.int32, "hull_cnt")
+        b = pp.shape[0]
+        if obs is None:
+            obs, obs_cnt = np.zeros([b, 1, 3]), np.zeros(b, dtype=np.int32)
+        ob, oc = _c(obs, np.float64, "obs"), _c(obs_cnt, np.int32, "obs_cnt")
+        self.n_bank, self.np, self.nseg1, self.hmax, self.pomax = b, pp.shape[1], sp.shape[1], hl.shape[1], ob.shape[1]
+        self._h = ctypes.c_void_p()
+        check(lib().ppnet_bank_upload(ctypes.c_int32(device), _p(pp), _p(sp), _p(hl), _p(hc), _p(ob), _p(oc),
+                                      ctypes.c_int32(b), ctypes.c_int32(self.np), ctypes.c_int32(self.nseg1),
+                                      ctypes.c_int32(self.hmax), ctypes.c_int32(self.pomax), ctypes.byref(self._h)),
+              "ppnet_bank_upload")
+
+    def close(self):
+        if self._h:
+            lib().ppnet_bank_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def generate_maps_host(ctx, bank, map0, n_maps, reps, obstacles_num, out, resolution=224, map_size=50.0,
+                       obstacle_size=5.0, clearance=1.0, seed=DEFAULT_SEED, max_tries=4096, raster_inflate=0.0):
+    """MapGenerate.generate into HOST arrays.  `out` is a dict of preallocated numpy arrays with any of the keys
+    angle f64[n], trans i32[n,2], segpt f64[n,S+1,2], pathpt f64[n,Np,2], obs f64[n,O+pomax,3], obs_cnt i32[n],
+    rand_cnt i32[n], bits u32[n,R,W], tries i32[n], valid u8[n], counters u64[4]."""
+    p = GenParams()
+    p.map0, p.n_maps, p.reps, p.obstacles_num, p.max_tries = map0, n_maps, reps, obstacles_num, max_tries
+    p.resolution, p.map_size, p.obstacle_size = float(resolution), float(map_size), float(obstacle_size)
+    p.clearance, p.raster_inflate, p.seed = float(clearance), float(raster_inflate), seed
+    for name in ("angle", "trans", "segpt", "pathpt", "obs", "obs_cnt", "rand_cnt", "bits", "tries", "valid"):
+        a = out.get(name)
+        setattr(p, "out_" + name, a.ctypes.data if a is not None else None)
+    cts = out.get("counters")
+    p.counters = cts.ctypes.data if cts is not None else None
+    check(lib().ppnet_generate_maps_host(ctx._h, bank._h, ctypes.byref(p)), "ppnet_generate_maps_host")
+    return out
