@@ -52,11 +52,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.first = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -66,13 +67,17 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """Samples before this call (start-up, warm-up) are dropped: only the timed region is reported."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[max(self.first - 1, 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -194,6 +199,7 @@ def run_ours(args):
     gmm_out = torch.empty([n_gmm, 2], dtype=torch.float32, device=dev)
     v64 = torch.empty(n_seg, dtype=torch.uint8, device=dev)
     v32 = torch.empty(n_seg, dtype=torch.uint8, device=dev)
+    vdda = torch.empty(n_seg, dtype=torch.uint8, device=dev)
     counters = torch.zeros([4], dtype=torch.int64, device=dev)
     gen = ops.generate_maps(bank, rank * M, M, REPS, O, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED, counters=counters,
                             raster_inflate=clear_px / 2)
@@ -209,7 +215,7 @@ def run_ours(args):
         if ev: ev[2].record()
         ops.segcheck_mpnet_f32(segs32, gen.obs, gen.obs_cnt, clear_px, out=v32)
         if ev: ev[3].record()
-        vd = ops.dda_gridcheck(gen.bits, R, segs32, want_first=False)
+        vd = ops.dda_gridcheck(gen.bits, R, segs32, want_first=False, out=vdda)
         if ev: ev[4].record()
         ops.gmm_sample(SEED, map0 * GMM_PER_MAP, n_gmm, g_mean, g_std, g_w, out=gmm_out)
         if ev: ev[5].record()
@@ -220,14 +226,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi attaching to the driver stalls kernel launches for
+    # several ms, which must not land inside the timed region; its 50 ms samples then cover warm-up + timed steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.6)
     for it in range(args.warmup):
         step(it)
     barrier()
     counters.zero_()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = _lib.launch_count()
+    sampler.mark()
     barrier()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -248,7 +258,10 @@ def run_ours(args):
     else:
         tot = counters.cpu().numpy()
     ms_step = ms_total / args.steps
-    k_ms = np.asarray([[e[i].elapsed_time(e[i + 1]) for i in range(5)] for e in evs]).mean(axis=0)
+    k_ms = np.asarray([[e[i].elapsed_time(e[i + 1]) for i in range(5)] for e in evs]).mean(axis=0)   # mean over the timed launches
+    if os.environ.get("PPNET_BENCH_DEBUG"):
+        for e in evs:
+            print(" ".join("%.3f" % e[i].elapsed_time(e[i + 1]) for i in range(5)), file=sys.stderr)
     maps_done, valid, acc_obs, tries = (int(x) for x in tot)
     seg_per_step = 3 * n_seg * world
     value = seg_per_step / (ms_step * 1e-3)
@@ -351,7 +364,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--maps", type=int, default=10000, help="maps per GPU per step")

@@ -5,12 +5,19 @@
 // verdict = first k whose cell is outside [0,R)^2 or occupied.
 //
 // One CTA per (map, chunk).  The map's bitmap (6 272 B at R = 224, 131 072 B at R = 1024) is pulled into
-// shared memory by ONE bulk async copy (cp.async.bulk -> UBLKCP on the TMA engine, completion on an mbarrier).
-// A warp owns a batch of 32 segments, one per lane.  Each lane walks its own segment with an exact
-// incremental form of the floor() above (remainder accumulators, no division); the warp leaves the loop as
-// soon as __ballot_sync says every lane is blocked or finished.  When only a few long segments survive
-// (dense maps: most lanes hit early), the stragglers are finished cooperatively: 32 cells per round across the
-// lanes, __ballot_sync picks the first blocked cell.
+// shared memory by ONE bulk async copy (cp.async.bulk -> UBLKCP on the TMA engine, completion on an mbarrier)
+// while the CTA's first segments are already being loaded (coalesced float4).
+//  1. park: every thread snaps its segments, tests the START cell, and resolves on the spot what needs no walk
+//     (NaN coordinate, start outside the map or on an occupied cell -- about half of all segments on dense
+//     maps).  The survivors are COMPACTED into a shared-memory stage with a warp ballot scan (one shared atomic
+//     per warp), already in walk form {bit address, last step, minor-axis remainder increments}.
+//  2. walk: the major axis moves one cell per step, the minor axis carries the remainder of the floor() above
+//     (no division; straight-line predicated code).  A lane that finishes (occupied cell, left the map, end
+//     reached) pulls the NEXT parked segment instead of idling until the slowest lane of its warp is done:
+//     __ballot_sync finds the idle lanes and ranks them, the warp claims stage entries 64 at a time.
+//     Walk lengths are wildly uneven, so this keeps ~all lanes busy where a fixed lane<->segment mapping kept
+//     a quarter of them busy.
+//  3. flush: results (first blocked step, -1 = free) are written back coalesced.
 #include "common.cuh"
 
 namespace ppnet {
@@ -22,20 +29,26 @@ __device__ __forceinline__ long long floordiv64(long long num, long long den) { 
 }
 
 constexpr int kDdaThreads = 256;
-constexpr int kCoordClamp = 1 << 29;
+constexpr int kDdaPerThread = 4;
+constexpr int kDdaStage = kDdaThreads * kDdaPerThread;   // segments per stage (16 KB of walk records)
+constexpr int kDdaClaim = 64;                // stage entries a warp claims at a time
+constexpr float kCoordClampF = 536870912.0f; // 2^29
 constexpr int kLaneWalkMaxN = 1 << 28;       // remainders stay inside int32
-constexpr int kStragglers = 4;               // <= this many live lanes ...
-constexpr int kCoopMinRemaining = 96;        // ... with more than this many cells left: finish them cooperatively
 
-__device__ __forceinline__ int snap(float v, bool& bad) {
-    if (!(v == v)) { bad = true; return 0; }
-    const double r = rint((double)v);                                      // A4 rule, step 1, offset 0
-    return (int)fmin(fmax(r, -(double)kCoordClamp), (double)kCoordClamp);
-}
+// A4 rule at step 1 / offset 0: rintf is round-half-to-even and exact (floats >= 2^23 are integers already), so
+// it equals rint((double)v); the clamp to +-2^29 is exact in float.
+__device__ __forceinline__ int snap(float v) { return (int)fminf(fmaxf(rintf(v), -kCoordClampF), kCoordClampF); }
 
-__device__ __forceinline__ bool cell_blocked(const uint32_t* __restrict__ bm, int R, int W, int cx, int cy) {
-    if ((unsigned)cx >= (unsigned)R || (unsigned)cy >= (unsigned)R) return true;
-    return (bm[cy * W + (cx >> 5)] >> (cx & 31)) & 1u;
+// over-long segments (n > 2^28; only reachable with coordinates far outside the map): division per cell, but the
+// walk leaves the map within R steps
+__device__ __noinline__ int walk_slow(const uint32_t* __restrict__ bm, int R, int W, int x0, int y0, int dx, int dy) {
+    const long long n = max(abs((long long)dx), abs((long long)dy));
+    for (long long k = 0; k <= n; ++k) {
+        const long long cx = x0 + floordiv64(2 * k * dx + n, 2 * n), cy = y0 + floordiv64(2 * k * dy + n, 2 * n);
+        if (cx < 0 || cx >= R || cy < 0 || cy >= R) return (int)k;
+        if ((bm[(int)cy * W + ((int)cx >> 5)] >> ((int)cx & 31)) & 1u) return (int)k;
+    }
+    return -1;
 }
 
 __global__ void __launch_bounds__(kDdaThreads)
@@ -43,7 +56,9 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
            const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
            uint8_t* __restrict__ verdict, int32_t* __restrict__ first_hit) {
     extern __shared__ __align__(128) unsigned char dsm[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);                      // 16 B header
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);                      // 16 B header: mbarrier, claim counter, parked count
+    int* next = reinterpret_cast<int*>(dsm + 8);
+    int* parked = reinterpret_cast<int*>(dsm + 12);
     uint32_t* bm = reinterpret_cast<uint32_t*>(dsm + 16);
     const int m = blockIdx.x;
     const int64_t lo = seg_off ? seg_off[m] : (int64_t)m * segs_per_map;
@@ -52,116 +67,159 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
     if (base >= hi) return;
     const int64_t end = min(hi, base + (int64_t)chunk);
     const uint32_t bytes = (uint32_t)(R * W * 4);
+    int4* stage = reinterpret_cast<int4*>(dsm + 16 + ((bytes + 15u) & ~15u));   // walk records of the parked segments
+    uint16_t* sidx = reinterpret_cast<uint16_t*>(stage + kDdaStage);           // their slot in the stage's result array
+    int16_t* res = reinterpret_cast<int16_t*>(sidx + kDdaStage);                // first blocked step per segment, -1 free
+    const bool bulk = (bytes & 15u) == 0;
 
-    if ((bytes & 15u) == 0) {
+    if (bulk) {
         // regular case: one bulk async copy (TMA engine; a contiguous block needs no tensor map)
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                          : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(bm)), "l"(bits + (size_t)m * R * W), "r"(bytes), "r"(smem_u32(bar))
                          : "memory");
         }
-    }
-
-    // while the copy is in flight: every lane loads and snaps its first segment
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int nwarps = kDdaThreads / 32;
-
-    if ((bytes & 15u) == 0) {
-        uint32_t done = 0;                                                 // wait for phase 0 (HW sleep, no spin on memory)
-        while (!done) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(done) : "r"(smem_u32(bar)) : "memory");
-        }
     } else {
         // odd-sized bitmaps (R*W not a multiple of 4 words) cannot use the bulk engine: plain loads
         const uint32_t* src = bits + (size_t)m * R * W;
         for (int i = threadIdx.x; i < R * W; i += kDdaThreads) bm[i] = __ldg(src + i);
-        __syncthreads();
     }
 
-    for (int64_t b0 = base + 32 * warp; b0 < end; b0 += 32 * nwarps) {
-        const int64_t mine = b0 + lane;                                    // 512 B coalesced per warp
-        int x0 = 0, y0 = 0, dx = 0, dy = 0, n = 0;
-        bool bad = false, have = mine < end;
-        if (have) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(segs) + mine);
-            x0 = snap(s.x, bad); y0 = snap(s.y, bad);
-            dx = snap(s.z, bad) - x0; dy = snap(s.w, bad) - y0;            // |d| <= 2^30 after the clamp
-            n = max(abs(dx), abs(dy));
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int RS = W * 32;                                                 // bits per bitmap row
+    for (int64_t st0 = base; st0 < end; st0 += kDdaStage) {
+        const int ns = (int)min((int64_t)kDdaStage, end - st0);
+        // ---- 1. park ----------------------------------------------------------------------------------------
+        float4 sv[kDdaPerThread];
+#pragma unroll
+        for (int j = 0; j < kDdaPerThread; ++j) {                          // all loads in flight before the first use
+            const int t = threadIdx.x + j * kDdaThreads;
+            sv[j] = t < ns ? __ldg(reinterpret_cast<const float4*>(segs) + st0 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        int first = -1;                                                    // first blocked k of MY segment
-        bool live = have;
-        if (have && bad) { first = 0; live = false; }                      // NaN coordinate: blocked at k = 0
-        const bool lane_walk_ok = n <= kLaneWalkMaxN;
+        if (threadIdx.x == 0) { *next = 0; *parked = 0; }
+        __syncthreads();                                                   // orders the barrier init / plain bitmap loads / counters
+        if (st0 == base && bulk) {
+            uint32_t done = 0;                                             // wait for phase 0 (HW sleep, no spin on memory)
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kDdaPerThread; ++j) {
+            const int t = threadIdx.x + j * kDdaThreads;
+            const float4 s = sv[j];
+            const bool have = t < ns;
+            const bool nan = !(s.x == s.x && s.y == s.y && s.z == s.z && s.w == s.w);
+            const int x0 = snap(s.x), y0 = snap(s.y);
+            const int dx = snap(s.z) - x0, dy = snap(s.w) - y0;            // |d| <= 2^30 after the clamp
+            const bool inside = (unsigned)x0 < (unsigned)R && (unsigned)y0 < (unsigned)R;
+            const int a = y0 * RS + x0;
+            bool blocked0 = nan || !inside;                                // NaN coordinate or start outside the map: blocked at k = 0
+            if (!blocked0) blocked0 = (bm[a >> 5] >> (a & 31)) & 1u;
+            const int adx = abs(dx), ady = abs(dy);
+            const int n = max(adx, ady);
+            int r0 = blocked0 ? 0 : (n == 0 ? -1 : -2);                    // -2: needs a walk
+            if (r0 == -2 && n > kLaneWalkMaxN) r0 = walk_slow(bm, R, W, x0, y0, dx, dy);
+            const bool walk = have && r0 == -2;
+            if (have && r0 != -2) res[t] = (int16_t)r0;
+            // compaction of the survivors: ballot scan inside the warp, one shared atomic per warp
+            const unsigned wm = __ballot_sync(0xffffffffu, walk);
+            int wb = 0;
+            if (lane == 0 && wm) wb = atomicAdd(parked, __popc(wm));
+            wb = __shfl_sync(0xffffffffu, wb, 0);
+            if (walk) {
+                const bool xmaj = adx >= ady;
+                const int dM = xmaj ? dx : dy, cM = xmaj ? x0 : y0;
+                const int kM = dM > 0 ? R - cM : cM + 1;                   // first k whose major coordinate is outside
+                const int kend = min(n, kM - 1);
+                const unsigned flags = (xmaj ? 1u : 0u) | (dM > 0 ? 2u : 0u) | (kM - 1 < n ? 4u : 0u);
+                const int pos = wb + __popc(wm & lt);
+                stage[pos] = make_int4((int)((unsigned)a | (flags << 28)), kend | ((xmaj ? y0 : x0) << 16),
+                                       2 * (xmaj ? dy : dx), 2 * n);
+                sidx[pos] = (uint16_t)t;
+            }
+        }
+        __syncthreads();
+        const int np_ = *parked;
 
-        // ---- phase 1: one lane per segment, exact incremental walk -------------------------------------
-        int k = 0, cx = x0, cy = y0;
-        int rx = n, ry = n;                                                // remainders of (2k d + n) mod 2n
-        const int n2 = 2 * n, dx2 = 2 * dx, dy2 = 2 * dy;
+        // ---- 2. walk: lanes pull parked segments until the stage is empty -----------------------------------
+        bool live = false, exhausted = np_ == 0, exitM = false;
+        int slot = 0, k = 0, kend = 0, a = 0, r = 0, n2 = 0, dm2 = 0, stepM = 0, stepm = 0, cm = 0;
+        int wnext = 0, wend = 0;                                           // this warp's claimed range (warp-uniform)
         for (;;) {
-            const unsigned alive = __ballot_sync(0xffffffffu, live && lane_walk_ok);
-            if (!alive) break;                                             // every lane blocked or finished
-            if (__popc(alive) <= kStragglers) {                            // few survivors with a long way to go?
-                const int rem = (live && lane_walk_ok) ? n - k : 0;
-                if (__reduce_max_sync(0xffffffffu, rem) > kCoopMinRemaining) break;
+            const unsigned need = __ballot_sync(0xffffffffu, !live);
+            if (need && !exhausted) {
+                if (wnext >= wend) {
+                    // guided self-scheduling: big claims first, small ones near the end (short tail per warp)
+                    const int c = max(8, min(kDdaClaim, (np_ - wend) >> 4));
+                    int b = 0;
+                    if (lane == 0) b = atomicAdd(next, c);
+                    b = __shfl_sync(0xffffffffu, b, 0);
+                    wnext = b;
+                    wend = min(b + c, np_);
+                    exhausted = b >= np_;
+                }
+                if (!exhausted) {
+                    const int my = wnext + __popc(need & lt);
+                    if (!live && my < wend) {
+                        const int4 q = stage[my];
+                        slot = sidx[my];
+                        const unsigned flags = (unsigned)q.x >> 28;
+                        a = q.x & 0x0fffffff;
+                        kend = q.y & 0xffff;
+                        cm = q.y >> 16;
+                        dm2 = q.z;
+                        n2 = q.w;
+                        r = n2 >> 1;
+                        stepM = ((flags & 2u) ? 1 : -1) * ((flags & 1u) ? 1 : RS);
+                        stepm = (flags & 1u) ? RS : 1;
+                        exitM = flags & 4u;
+                        k = 0;
+                        live = true;
+                    }
+                    wnext = min(wend, wnext + __popc(need));
+                }
+            }
+            if (!__any_sync(0xffffffffu, live)) {
+                if (exhausted) break;
+                continue;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {                                  // 4 cells between two warp votes
-                if (live && lane_walk_ok) {
-                    if (cell_blocked(bm, R, W, cx, cy)) { first = k; live = false; }
-                    else if (k == n) { live = false; }                    // reached the end cell: free
-                    else {
-                        ++k;
-                        rx += dx2; ry += dy2;
-                        if (rx >= n2) { rx -= n2; ++cx; } else if (rx < 0) { rx += n2; --cx; }
-                        if (ry >= n2) { ry -= n2; ++cy; } else if (ry < 0) { ry += n2; --cy; }
-                    }
-                }
+            for (int u = 0; u < 4; ++u) {                                  // 4 cells between two warp votes; straight-line code
+                const bool in = live && (unsigned)cm < (unsigned)R;       // minor coordinate still inside?
+                uint32_t word = 0xffffffffu;
+                if (in) word = bm[a >> 5];
+                const bool blocked = (word >> (a & 31)) & 1u;              // occupied, or outside by the minor axis
+                const bool done = live && (blocked || k == kend);
+                // at kend and free: the next cell leaves by the major axis (blocked at k+1) or the end was reached (free)
+                if (done) res[slot] = (int16_t)(blocked ? k : (exitM ? k + 1 : -1));
+                live = live && !done;
+                ++k;                                                       // (a finished lane's state is dead; advancing it is harmless)
+                a += stepM;
+                r += dm2;
+                const bool up = r >= n2, dn = r < 0;
+                r += (dn ? n2 : 0) - (up ? n2 : 0);
+                a += (up ? stepm : 0) - (dn ? stepm : 0);
+                cm += (int)up - (int)dn;
             }
         }
-
-        // ---- phase 2: stragglers (and over-long segments), 32 cells per round across the warp ----------
-        unsigned todo = __ballot_sync(0xffffffffu, live);
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int sx0 = __shfl_sync(0xffffffffu, x0, j), sy0 = __shfl_sync(0xffffffffu, y0, j);
-            const long long sdx = __shfl_sync(0xffffffffu, dx, j), sdy = __shfl_sync(0xffffffffu, dy, j);
-            const long long sn = __shfl_sync(0xffffffffu, n, j);
-            const long long kstart = __shfl_sync(0xffffffffu, k, j);       // cells < kstart were already free
-            int f = -1;
-            for (long long k0 = kstart; k0 <= sn; k0 += 32) {
-                const long long kk = k0 + lane;
-                bool blocked = false;
-                if (kk <= sn) {
-                    long long ccx = sx0, ccy = sy0;
-                    if (sn) {
-                        ccx += floordiv64(2 * kk * sdx + sn, 2 * sn);
-                        ccy += floordiv64(2 * kk * sdy + sn, 2 * sn);
-                    }
-                    blocked = (ccx < 0 || ccx >= R || ccy < 0 || ccy >= R) ? true
-                              : (bool)((bm[(int)ccy * W + ((int)ccx >> 5)] >> ((int)ccx & 31)) & 1u);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, blocked);
-                if (bal) { f = (int)k0 + (__ffs(bal) - 1); break; }        // early exit for the whole warp
-            }
-            if (lane == j) { first = f; live = false; }
+        __syncthreads();
+        // ---- 3. flush the stage's results (coalesced) ----------------------------------------------------------
+        for (int t = threadIdx.x; t < ns; t += kDdaThreads) {
+            const int rr = res[t];
+            verdict[st0 + t] = (uint8_t)(rr >= 0);
+            if (first_hit) first_hit[st0 + t] = rr;
         }
-
-        if (have) {
-            verdict[mine] = (uint8_t)(first >= 0);
-            if (first_hit) first_hit[mine] = first;
-        }
+        __syncthreads();                                                   // res / stage are rewritten by the next stage
     }
 }
 
@@ -181,7 +239,7 @@ extern "C" int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int
     const size_t bm_bytes = (size_t)resolution * W * 4;
     PPNET_REQUIRE((reinterpret_cast<uintptr_t>(bits) & 15) == 0 && (reinterpret_cast<uintptr_t>(segs_xy) & 15) == 0,
                   "dda: bits and segs must be 16-byte aligned");
-    const size_t smem = bm_bytes + 16;
+    const size_t smem = ((bm_bytes + 15) & ~(size_t)15) + 16 + (size_t)kDdaStage * (16 + 2 + 2);
     PPNET_REQUIRE(smem <= 220 * 1024, "dda: resolution too large for a shared-memory bitmap");
     // big bitmaps: amortise the staging over every segment of the map; small ones: more CTAs in flight
     const int chunk = bm_bytes >= 64 * 1024 ? 8192 : 1024;

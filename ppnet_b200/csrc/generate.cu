@@ -26,7 +26,7 @@
 
 namespace ppnet {
 
-constexpr int kGenThreads = 256;
+constexpr int kGenThreads = 128;
 constexpr int kGenWarps = kGenThreads / 32;
 constexpr int kBlkPts = 16;
 

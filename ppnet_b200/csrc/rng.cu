@@ -7,6 +7,8 @@
 // Here every draw is a pure function of (seed, stream id, unit index, block), so any sharding of the
 // index range over GPUs reproduces the same numbers.  Parity with the reference is statistical
 // (tests: chi^2 on component frequencies, KS on both marginals) -- SURVEY 8(a) A17.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ppnet {
@@ -56,13 +58,13 @@ gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const fl
     const bool cache = D <= 4;
     if (cache) for (int i = threadIdx.x; i < K * D; i += blockDim.x) { s_mean[i] = mean[i]; s_std[i] = stdv[i]; }
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // persistent grid-stride loop: the CDF / parameter staging above is paid once per CTA, not once per 256 samples
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t g = sample0 + (uint64_t)i;
     uint4 r = Philox::gen(key, make_uint4(0u, STREAM_GMM_SAMPLE, (uint32_t)g, (uint32_t)(g >> 32)));
     const float uc = u24(r.x);
-    int k = 0;
-    while (k < K - 1 && uc >= cdf[k]) ++k;                // inverse CDF
+    int k = 0;                                            // inverse CDF: the CDF is non-decreasing, so the first k with
+    for (int j = 0; j < K - 1; ++j) k += (uc >= cdf[j]);  // uc < cdf[k] is the count of entries <= uc (branch-free)
     if (comp) comp[i] = k;
     uint32_t wa = r.y, wb = r.z;
     for (int d = 0; d < D; d += 2) {
@@ -87,6 +89,7 @@ gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const fl
             const float s1 = cache ? s_std[k * D + d + 1] : stdv[k * D + d + 1];
             out[i * D + d + 1] = m1 + s1 * (rad * sn);
         }
+    }
     }
 }
 
@@ -127,7 +130,8 @@ extern "C" int ppnet_gmm_sample(uint64_t seed, uint64_t sample0, int64_t n, int3
     PPNET_REQUIRE(dim > 0 && dim <= 1026, "gmm_sample: bad dim");
     if (n == 0) return PPNET_OK;
     PPNET_REQUIRE(mean && stdv && weights && out, "gmm_sample: null pointer");
-    gmm_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_key(seed), sample0, n,
+    const int64_t ctas = std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 8);
+    gmm_sample_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(make_key(seed), sample0, n,
                                                                                     order, dim, mean, stdv, weights,
                                                                                     out, comp);
     PPNET_LAUNCH_CHECK("gmm_sample_kernel");

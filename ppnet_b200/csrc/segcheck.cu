@@ -130,34 +130,108 @@ __device__ __forceinline__ Circle<T> make_circle(const double* __restrict__ o, d
     return c;
 }
 
-constexpr int kCircTile = 128;       // circles staged per pass
+constexpr int kCircTile = 128;       // circles staged per pass (one bit each in a 128-bit candidate mask)
 constexpr int kSegThreads = 256;
-template <typename T> struct SegCfg;      // segments per thread: registers (f64) vs ILP (f32)
-template <> struct SegCfg<double> { static constexpr int kPerThread = 1; };
-template <> struct SegCfg<float> { static constexpr int kPerThread = 2; };
 
-// ---- exact-safe spatial culling -------------------------------------------------------------------------
-// A circle can only collide with a segment whose bounding box meets the circle's box inflated by thr:
-//   vertex test  |e - o| < thr            => o is within thr of the endpoint e,
-//   edge test    |dis| < thr and the foot of the perpendicular strictly between s and e
-//                                         => o is within thr of a point of the segment.
-// Both boxes are further inflated by a margin thousands of ulps wide (kCull * magnitude), so a pair that the
-// grid separates is separated by far more than any rounding of the reference's operation sequence could
-// bridge (for the edge test the foot then lies beyond an end by >= the margin, where normalised
-// (p-s).(p-e) is within 1e-6 of +1).  Culled pairs are exactly the pairs whose verdict is "no".
-// The staged circles are binned into an 8x8 grid over [0, bound]^2 (cell lists in shared memory); a segment
-// only walks the lists of the cells its box touches.  The bin function is monotone, so two intersecting
-// intervals always share a bin.  Long segments (box > kMaxQueryCells bins) and non-finite coordinates take
-// the plain loop over all staged circles.
-constexpr int kGridN = 8;
-constexpr int kGridCells = kGridN * kGridN;
-constexpr int kMaxQueryCells = 12;
-template <typename T> struct Cull;
-template <> struct Cull<double> { static constexpr double k = 1e-9; };
-template <> struct Cull<float> { static constexpr float k = 1e-3f; };
+// ---- the fast path: exact-safe culling + division-free decisions ----------------------------------------
+// Notation: u = unit roundoff of the flavour, Mg = |s|_1 + |e|_1 + |o|_1 + thr + 1 (bounds every length in
+// the pair), E = 50 u Mg = the reach of the reference's accumulated rounding (its `dis` is within 7u Mg of
+// the real-arithmetic value of the same expression on the same rounded d = e-s, q = o-s; the sign of its
+// normalised (p-s).(p-e) is certain once the foot is >= 4x the error of p away from both ends), and
+// delta = eps Mg with eps >= 10x E/Mg plus the error of the approximate L used below.
+//   far:      |cross(q,d)| > (thr + delta) L                  => |dis| > thr + E       => reference says no
+//   outside:  q.d < -delta L  or  q.d > |d|^2 + delta L       => foot beyond an end    => reference says no
+//   inside:   |cross| < (thr - delta) L and delta L < q.d < |d|^2 - delta L           => reference says yes
+// Anything else (a fraction ~eps of the near pairs) replays the reference's operation sequence verbatim, and
+// so does every pair with a non-finite / huge / degenerate operand.  The filter arithmetic may round any
+// way it likes (its own error is part of delta).
+// Culling: circle boxes inflated by thr + eps*mc and segment-piece boxes inflated by eps*ms are binned
+// separably (32 x-bins, 32 y-bins, one 128-bit circle mask per bin); box intersection on a grid is
+// separable, so  cand = OR_x(xmask) & OR_y(ymask)  is exactly the set of circles whose box meets the
+// piece's box.  A culled circle is farther than thr + delta (in the max norm, hence Euclidean) from every
+// point of the segment: the vertex test fails, and either the foot is inside (|dis| >= thr + delta), or
+// outside by >= E (sign certain), or within E of an end (|dis| >= thr + delta - E/2): the reference says no.
+template <typename T> struct Filt;
+template <> struct Filt<double> {
+    static constexpr double eps = 4e-6;      // L comes from a float sqrt (rel. 1.2e-7): 30x over it
+    static constexpr double lim = 1e15, tiny = 1e-30;
+};
+template <> struct Filt<float> {
+    static constexpr float eps = 5e-5f;      // E/Mg = 50 * 2^-24 = 3e-6
+    static constexpr float lim = 1e8f, tiny = 1e-20f;
+};
+constexpr int kBins = 32;
 
-__device__ __forceinline__ int bin_of(float v, float scale) {          // monotone non-decreasing in v
-    return (int)fminf(fmaxf(v * scale, 0.0f), (float)(kGridN - 1));
+struct Mask128 {
+    uint32_t w[4];
+};
+__device__ __forceinline__ int bin_clamp(float b) {                     // monotone non-decreasing in b
+    return (int)fminf(fmaxf(b, 0.0f), (float)(kBins - 1));
+}
+
+// Per-segment state of the fast path (no division, no exact square root)
+template <typename T>
+struct FastSeg {
+    T s0, s1, e0, e1;   // (x, y) after the flavour's swap
+    T d0, d1, L2, L;    // d = e - s (rounded once, as the reference does), |d|^2, approximate |d|
+    T es;               // eps * (|s|_1 + |e|_1 + 1)
+    bool oob, verbatim;
+};
+
+template <typename T, bool SWAP>
+__device__ __forceinline__ FastSeg<T> fast_setup(T a0, T a1, T b0, T b1, T bound) {
+    using F = FP<T>;
+    FastSeg<T> g;
+    g.oob = (a0 < T(0)) || (a1 > bound) || (b0 < T(0)) || (b1 > bound);
+    if (SWAP) { g.s0 = a1; g.s1 = a0; g.e0 = b1; g.e1 = b0; }
+    else      { g.s0 = a0; g.s1 = a1; g.e0 = b0; g.e1 = b1; }
+    g.d0 = F::sub(g.e0, g.s0);
+    g.d1 = F::sub(g.e1, g.s1);
+    g.L2 = g.d0 * g.d0 + g.d1 * g.d1;
+    g.L = (T)sqrtf((float)g.L2);
+    const T ms = F::abs_(g.s0) + F::abs_(g.s1) + F::abs_(g.e0) + F::abs_(g.e1) + T(1);
+    g.es = Filt<T>::eps * ms;
+    g.verbatim = !(ms < Filt<T>::lim) || !(g.L2 > Filt<T>::tiny);      // NaN / inf / huge / degenerate
+    return g;
+}
+
+// The reference's edge test, operation for operation (process_map.py:401-417 / neuralplanner.py:55-68)
+template <typename T, int MODE>
+__device__ __noinline__ bool edge_exact(T s0, T s1, T e0, T e1, T ox, T oy, T thr) {
+    using F = FP<T>;
+    const T d0 = F::sub(e0, s0), d1 = F::sub(e1, s1);
+    const T L = F::sqrt_(Dot<T, MODE>::f(d0, d1, d0, d1));
+    const T n0 = F::div(d1, L), n1 = F::div(-d0, L);
+    const T q0 = F::sub(ox, s0), q1 = F::sub(oy, s1);
+    const T dis = Dot<T, MODE>::f(n0, n1, q0, q1);
+    if (!(F::abs_(dis) < thr)) return false;
+    const T p0 = F::sub(ox, F::mul(dis, n0)), p1 = F::sub(oy, F::mul(dis, n1));
+    T u0 = F::sub(p0, s0), u1 = F::sub(p1, s1);
+    const T nu = F::sqrt_(Dot<T, MODE>::f(u0, u1, u0, u1));
+    u0 = F::div(u0, nu); u1 = F::div(u1, nu);
+    T w0 = F::sub(p0, e0), w1 = F::sub(p1, e1);
+    const T nw = F::sqrt_(Dot<T, MODE>::f(w0, w1, w0, w1));
+    w0 = F::div(w0, nw); w1 = F::div(w1, nw);
+    return Dot<T, MODE>::f(u0, u1, w0, w1) < T(0);
+}
+
+template <typename T, int MODE>
+__device__ __forceinline__ bool fast_pair(const FastSeg<T>& g, const Circle<T>& c, T em, bool exact_only) {
+    using F = FP<T>;
+    // vertex test on e only, exact:  euclidean(e, o) < thr  <=>  rn(rn(v0^2) + rn(v1^2)) < T2
+    const T v0 = F::sub(g.e0, c.ox), v1 = F::sub(g.e1, c.oy);
+    if (F::add(F::mul(v0, v0), F::mul(v1, v1)) < c.T2) return true;
+    if (!exact_only) {
+        const T q0 = F::sub(c.ox, g.s0), q1 = F::sub(c.oy, g.s1);
+        const T ac = F::abs_(q0 * g.d1 - q1 * g.d0);
+        const T del = g.es + em;
+        if (ac > (c.thr + del) * g.L) return false;                    // far
+        const T tt = q0 * g.d0 + q1 * g.d1;
+        const T dl = del * g.L;
+        if (tt < -dl || tt > g.L2 + dl) return false;                  // foot beyond an end
+        if (ac < (c.thr - del) * g.L && tt > dl && tt < g.L2 - dl) return true;   // inside
+    }
+    return edge_exact<T, MODE>(g.s0, g.s1, g.e0, g.e1, c.ox, c.oy, c.thr);
 }
 
 template <typename T> struct Vec4;   // 4 coordinates of one segment
@@ -175,107 +249,196 @@ template <> struct Vec4<float> {
     }
 };
 
-// grid = (n_maps, chunks_per_map_max)
+// ---- kernel -----------------------------------------------------------------------------------------------
+// grid = (n_maps, chunks_per_map_max).  One CTA owns `chunk` consecutive segments of one map.
+//  1. staging (once per CTA): circles -> decision form; per axis two prefix tables over the 32 bins,
+//     LT[b] = circles whose box ends before bin b, GT[b] = circles whose box starts after bin b, so the set
+//     of circles meeting a bin range [b0, b1] is ~(LT[b0] | GT[b1]): four 128-bit loads per segment piece.
+//  2. each warp takes batches of 32 segments, one per lane: setup + candidate mask (converged code);
+//  3. the (segment, candidate circle) pairs of the whole batch go through a per-warp shared-memory queue and
+//     are evaluated 32 at a time whatever their owner: a lane with 9 candidates no longer holds back 31 lanes
+//     with one.  Hits are OR-ed into a per-warp mask; a pair whose segment already hit is skipped.
+constexpr int kSegWarps = kSegThreads / 32;
+constexpr int kQueueCap = 512;                   // pairs per round (16 per lane)
+constexpr int kTakeMax = kQueueCap / 32;
+
+template <typename T>
+struct __align__(16) SegSlot {                   // what a pair needs of its segment (d, |d|^2 are recomputed)
+    T s0, s1, e0, e1, L, es;                     // L == 0 marks a verbatim-only segment
+};
+
 template <typename T, int MODE, bool SWAP, bool STEER>
-__global__ void __launch_bounds__(kSegThreads)
-segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, int64_t segs_per_map,
+__global__ void __launch_bounds__(kSegThreads, 3)
+segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
                 const double* __restrict__ obs, const int32_t* __restrict__ obs_cnt, int omax,
                 double clearance, T bound, uint8_t* __restrict__ verdict, uint8_t* __restrict__ steer) {
-    constexpr int kSegPerThread = SegCfg<T>::kPerThread;
-    constexpr int kSegChunk = kSegThreads * kSegPerThread;
     const int m = blockIdx.x;
     const int64_t lo = seg_off ? seg_off[m] : (int64_t)m * segs_per_map;
     const int64_t hi = seg_off ? seg_off[m + 1] : lo + segs_per_map;
-    const int64_t base = lo + (int64_t)blockIdx.y * kSegChunk;
+    const int64_t base = lo + (int64_t)blockIdx.y * chunk;
     if (base >= hi) return;                       // whole CTA exits together
+    const int64_t end = min(hi, base + (int64_t)chunk);
 
     __shared__ Circle<T> sc[kCircTile];
-    __shared__ uint8_t cell_idx[kGridCells][kCircTile];
-    __shared__ int cell_cnt[kGridCells];
+    __shared__ T sem[kCircTile];                  // eps * (|o|_1 + thr)
+    __shared__ uint4 edge_lo[2][kBins], edge_hi[2][kBins];   // circles whose box starts / ends in this bin (x, y)
+    __shared__ uint4 LT[2][kBins], GT[2][kBins];
+    __shared__ uint32_t live_mask[4];             // circles that can ever answer "hit" (thr > 0)
+    __shared__ uint32_t odd_mask[4];              // ... of those, the ones that always take the verbatim path
+    __shared__ SegSlot<T> slot[kSegWarps][32];
+    __shared__ uint16_t queue[kSegWarps][kQueueCap];
+    __shared__ uint32_t hitmask[kSegWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cnt = min(obs_cnt[m], omax);
-    const bool use_grid = bound > T(0) && bound < T(1e30);
-    const float bscale = use_grid ? (float)kGridN / (float)bound : 0.0f;
+    const bool use_grid = bound > T(0) && bound < T(1e6);
+    const float bscale = use_grid ? (float)kBins / (float)bound : 0.0f;
     const double* __restrict__ mobs = obs + (size_t)m * omax * 3;
 
-    SegState<T> g[kSegPerThread];
-    bool live[kSegPerThread], hit[kSegPerThread];
-#pragma unroll
-    for (int k = 0; k < kSegPerThread; ++k) {
-        const int64_t i = base + threadIdx.x + (int64_t)k * kSegThreads;
-        live[k] = i < hi;
-        hit[k] = false;
-        if (live[k]) {
-            T a0, a1, b0, b1;
-            Vec4<T>::load(pts + 4 * i, a0, a1, b0, b1);
-            g[k] = seg_setup<T, MODE, SWAP>(a0, a1, b0, b1, bound);
-            hit[k] = g[k].oob;                    // `return True` before any circle is looked at
-        }
-    }
+    // first segment of this lane: its load is in flight while the circles are staged
+    int64_t i = base + 32 * warp + lane;
+    T a0 = T(0), a1 = T(0), b0 = T(0), b1 = T(0);
+    if (i < end) Vec4<T>::load(pts + 4 * i, a0, a1, b0, b1);
 
-    for (int t0 = 0; t0 < cnt; t0 += kCircTile) {
-        const int nt = min(kCircTile, cnt - t0);
+    for (int t0 = 0; t0 == 0 || t0 < cnt; t0 += kCircTile) {
+        const int nt = max(0, min(kCircTile, cnt - t0));
+        const bool first_tile = t0 == 0, last_tile = t0 + kCircTile >= cnt;
         __syncthreads();
-        if (threadIdx.x < kGridCells) cell_cnt[threadIdx.x] = 0;
+        if (threadIdx.x < 4 * kBins) {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            (threadIdx.x < 2 * kBins ? &edge_lo[0][0] : &edge_hi[0][0] - 2 * kBins)[threadIdx.x] = z;
+        }
+        if (threadIdx.x < 4) { live_mask[threadIdx.x] = 0u; odd_mask[threadIdx.x] = 0u; }
         __syncthreads();
         if (threadIdx.x < nt) {
-            const Circle<T> c = make_circle<T>(mobs + 3 * (t0 + threadIdx.x), clearance);
-            sc[threadIdx.x] = c;
-            // circles that can never answer "hit" (thr <= 0 or NaN, non-finite centre) are not binned at all
-            if (use_grid && c.thr > T(0) && FP<T>::abs_(c.ox) < T(1e30) && FP<T>::abs_(c.oy) < T(1e30)) {
-                const T h = c.thr + Cull<T>::k * (FP<T>::abs_(c.ox) + FP<T>::abs_(c.oy) + c.thr + bound);
-                const int x0 = bin_of((float)(c.ox - h), bscale), x1 = bin_of((float)(c.ox + h), bscale);
-                const int y0 = bin_of((float)(c.oy - h), bscale), y1 = bin_of((float)(c.oy + h), bscale);
-                for (int by = y0; by <= y1; ++by)
-                    for (int bx = x0; bx <= x1; ++bx) {
-                        const int cell = by * kGridN + bx;
-                        cell_idx[cell][atomicAdd(&cell_cnt[cell], 1)] = (uint8_t)threadIdx.x;
-                    }
+            const int j = threadIdx.x;
+            const Circle<T> c = make_circle<T>(mobs + 3 * (t0 + j), clearance);
+            sc[j] = c;
+            const uint32_t bit = 1u << (j & 31);
+            const int w = j >> 5;
+            if (c.thr > T(0)) {                   // thr <= 0 or NaN: neither test can ever be true
+                atomicOr(&live_mask[w], bit);
+                const T mc = FP<T>::abs_(c.ox) + FP<T>::abs_(c.oy) + c.thr;
+                const T em = Filt<T>::eps * mc;
+                sem[j] = em;
+                if (!(mc < Filt<T>::lim)) {
+                    atomicOr(&odd_mask[w], bit);  // NaN / inf / huge: never culled, always verbatim
+                } else if (use_grid) {
+                    const T h = c.thr + em;
+                    const int x0 = bin_clamp((float)(c.ox - h) * bscale - 2e-3f), x1 = bin_clamp((float)(c.ox + h) * bscale + 2e-3f);
+                    const int y0 = bin_clamp((float)(c.oy - h) * bscale - 2e-3f), y1 = bin_clamp((float)(c.oy + h) * bscale + 2e-3f);
+                    atomicOr(reinterpret_cast<uint32_t*>(&edge_lo[0][x0]) + w, bit);
+                    atomicOr(reinterpret_cast<uint32_t*>(&edge_hi[0][x1]) + w, bit);
+                    atomicOr(reinterpret_cast<uint32_t*>(&edge_lo[1][y0]) + w, bit);
+                    atomicOr(reinterpret_cast<uint32_t*>(&edge_hi[1][y1]) + w, bit);
+                }
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kSegPerThread; ++k) {
-            if (!live[k] || hit[k]) continue;
-            const SegState<T>& q = g[k];
-            bool brute = !use_grid;
-            int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-            if (!brute) {
-                const T ms = Cull<T>::k * (q.mag + bound);
-                const T lox = (q.s0 < q.e0 ? q.s0 : q.e0) - ms, hix = (q.s0 < q.e0 ? q.e0 : q.s0) + ms;
-                const T loy = (q.s1 < q.e1 ? q.s1 : q.e1) - ms, hiy = (q.s1 < q.e1 ? q.e1 : q.s1) + ms;
-                // NaN / inf coordinates fail this test and take the plain loop
-                if (!(FP<T>::abs_(lox) < T(1e30) && FP<T>::abs_(hix) < T(1e30) && FP<T>::abs_(loy) < T(1e30) &&
-                      FP<T>::abs_(hiy) < T(1e30))) brute = true;
-                else {
-                    x0 = bin_of((float)lox, bscale); x1 = bin_of((float)hix, bscale);
-                    y0 = bin_of((float)loy, bscale); y1 = bin_of((float)hiy, bscale);
-                    if ((x1 - x0 + 1) * (y1 - y0 + 1) > kMaxQueryCells) brute = true;
+        if (threadIdx.x < 4 * kBins) {            // prefix tables: (axis, which, bin) per thread
+            const int axis = (threadIdx.x >> 5) & 1, which = threadIdx.x >> 6, bin = threadIdx.x & 31;
+            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+            if (which == 0) {
+                for (int b = 0; b < bin; ++b) { const uint4 t = edge_hi[axis][b]; acc.x |= t.x; acc.y |= t.y; acc.z |= t.z; acc.w |= t.w; }
+                LT[axis][bin] = acc;
+            } else {
+                for (int b = bin + 1; b < kBins; ++b) { const uint4 t = edge_lo[axis][b]; acc.x |= t.x; acc.y |= t.y; acc.z |= t.z; acc.w |= t.w; }
+                GT[axis][bin] = acc;
+            }
+        }
+        __syncthreads();
+        const uint32_t lv0 = live_mask[0], lv1 = live_mask[1], lv2 = live_mask[2], lv3 = live_mask[3];
+        const uint32_t od0 = odd_mask[0], od1 = odd_mask[1], od2 = odd_mask[2], od3 = odd_mask[3];
+        if (!first_tile) { i = base + 32 * warp + lane; if (i < end) Vec4<T>::load(pts + 4 * i, a0, a1, b0, b1); }
+
+        // warp-uniform loop over this warp's batches of 32 segments
+        for (int64_t batch = base + 32 * warp; batch < end; batch += kSegThreads) {
+            const bool have = i < end;
+            const FastSeg<T> q = fast_setup<T, SWAP>(a0, a1, b0, b1, bound);
+            const int64_t cur = i;
+            i += kSegThreads;
+            if (i < end) Vec4<T>::load(pts + 4 * i, a0, a1, b0, b1);      // next batch's load overlaps this one's work
+            bool hit = !have || (first_tile ? q.oob : (verdict[cur] != 0));   // later tiles continue from the stored verdict
+            uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+            if (!hit && nt > 0) {
+                if (q.verbatim || !use_grid) {
+                    c0 = lv0; c1 = lv1; c2 = lv2; c3 = lv3;
+                } else {
+                    // pieces <= 3 bins long (one box for most short segments); each box is inflated by the margin + float slop
+                    const float sx = (float)q.s0 * bscale, sy = (float)q.s1 * bscale;
+                    const float dx = (float)q.d0 * bscale, dy = (float)q.d1 * bscale;
+                    const float mb = (float)q.es * bscale + 2e-3f;
+                    const int np_ = min(16, 1 + (int)(fmaxf(fabsf(dx), fabsf(dy)) * (1.0f / 3.0f)));
+                    const float inv = 1.0f / (float)np_;
+                    uint32_t n0 = ~0u, n1 = ~0u, n2 = ~0u, n3 = ~0u;       // circles culled by EVERY piece
+                    for (int pc = 0; pc < np_; ++pc) {
+                        const float ta = (float)pc * inv, tb = (float)(pc + 1) * inv;
+                        const float ax = sx + dx * ta, bx = sx + dx * tb, ay = sy + dy * ta, by = sy + dy * tb;
+                        const int x0 = bin_clamp(fminf(ax, bx) - mb), x1 = bin_clamp(fmaxf(ax, bx) + mb);
+                        const int y0 = bin_clamp(fminf(ay, by) - mb), y1 = bin_clamp(fmaxf(ay, by) + mb);
+                        const uint4 p = LT[0][x0], r = GT[0][x1], u = LT[1][y0], v = GT[1][y1];
+                        n0 &= p.x | r.x | u.x | v.x; n1 &= p.y | r.y | u.y | v.y;
+                        n2 &= p.z | r.z | u.z | v.z; n3 &= p.w | r.w | u.w | v.w;
+                    }
+                    c0 = lv0 & (~n0 | od0); c1 = lv1 & (~n1 | od1); c2 = lv2 & (~n2 | od2); c3 = lv3 & (~n3 | od3);
                 }
             }
-            if (brute) { x0 = x1 = y0 = y1 = 0; }                  // one pseudo-bin holding every staged circle
-            for (int by = y0; by <= y1 && !hit[k]; ++by)
-                for (int bx = x0; bx <= x1 && !hit[k]; ++bx) {
-                    const int cell = by * kGridN + bx;
-                    const int nc = brute ? nt : cell_cnt[cell];
-                    for (int t = 0; t < nc; ++t) {
-                        const int j = brute ? t : (int)cell_idx[cell][t];
-                        if (pair_hit<T, MODE>(q, sc[j])) { hit[k] = true; break; }
-                    }
-                }
-        }
-    }
-
+            {
+                SegSlot<T> sl;
+                sl.s0 = q.s0; sl.s1 = q.s1; sl.e0 = q.e0; sl.e1 = q.e1; sl.es = q.es;
+                sl.L = q.verbatim ? T(0) : q.L;
+                slot[warp][lane] = sl;
+            }
+            if (lane == 0) hitmask[warp] = 0u;
+            // rounds of <= kQueueCap pairs (one round unless some lane has > 16 candidates)
+            while (__any_sync(0xffffffffu, (c0 | c1 | c2 | c3) != 0u)) {
+                const int mine = min(kTakeMax, __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3));
+                int off = mine;                                            // inclusive warp scan
 #pragma unroll
-    for (int k = 0; k < kSegPerThread; ++k) {
-        const int64_t i = base + threadIdx.x + (int64_t)k * kSegThreads;
-        if (!live[k]) continue;
-        if (verdict) verdict[i] = hit[k] ? 1 : 0;
-        if (STEER && steer) {
-            // steerTo: dist = euclidean(start, end) in f32 (un-fused); 0 iff dist > 0 and blocked
-            using F = FP<T>;
-            const T x = F::sub(g[k].s0, g[k].e0), y = F::sub(g[k].s1, g[k].e1);
-            const T dist = F::sqrt_(F::add(F::mul(x, x), F::mul(y, y)));
-            steer[i] = (dist > T(0) && hit[k]) ? 0 : 1;
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, off, sft);
+                    if (lane >= sft) off += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, off, 31);
+                off -= mine;
+                __syncwarp();
+                for (int t = 0; t < mine; ++t) {
+                    int j;
+                    if (c0) { const int b = __ffs(c0) - 1; c0 &= c0 - 1; j = b; }
+                    else if (c1) { const int b = __ffs(c1) - 1; c1 &= c1 - 1; j = 32 + b; }
+                    else if (c2) { const int b = __ffs(c2) - 1; c2 &= c2 - 1; j = 64 + b; }
+                    else { const int b = __ffs(c3) - 1; c3 &= c3 - 1; j = 96 + b; }
+                    queue[warp][off + t] = (uint16_t)((lane << 8) | j);
+                }
+                __syncwarp();
+                for (int k = lane; k < total; k += 32) {
+                    const int e = queue[warp][k];
+                    const int owner = e >> 8, j = e & 127;
+                    if ((*reinterpret_cast<volatile uint32_t*>(&hitmask[warp]) >> owner) & 1u) continue;
+                    const SegSlot<T> sl = slot[warp][owner];
+                    FastSeg<T> g;
+                    g.s0 = sl.s0; g.s1 = sl.s1; g.e0 = sl.e0; g.e1 = sl.e1; g.L = sl.L; g.es = sl.es;
+                    g.d0 = FP<T>::sub(g.e0, g.s0);
+                    g.d1 = FP<T>::sub(g.e1, g.s1);
+                    g.L2 = g.d0 * g.d0 + g.d1 * g.d1;
+                    const bool odd = ((j < 64 ? (j < 32 ? od0 : od1) : (j < 96 ? od2 : od3)) >> (j & 31)) & 1u;
+                    if (fast_pair<T, MODE>(g, sc[j], sem[j], !(sl.L > T(0)) || odd)) atomicOr(&hitmask[warp], 1u << owner);
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            if (have) {
+                hit = hit || ((hitmask[warp] >> lane) & 1u);
+                if (verdict && (last_tile || hit)) verdict[cur] = hit ? 1 : 0;
+                if (STEER && steer && last_tile) {
+                    // steerTo: dist = euclidean(start, end) in f32 (un-fused); 0 iff dist > 0 and blocked.
+                    // sqrt(x) > 0  <=>  x > 0  (and NaN stays false), so the root itself is not needed.
+                    using F = FP<T>;
+                    const T x = F::sub(q.s0, q.e0), y = F::sub(q.s1, q.e1);
+                    const T d2 = F::add(F::mul(x, x), F::mul(y, y));
+                    steer[cur] = (d2 > T(0) && hit) ? 0 : 1;
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -296,7 +459,7 @@ static int check_common(const T* pts, int64_t n_segs, const int64_t* seg_off, in
     return PPNET_OK;
 }
 
-// largest per-map segment count decides grid.x; with a CSR we cannot know it without a device
+// largest per-map segment count decides grid.y; with a CSR we cannot know it without a device
 // read, so the caller passes max_segs_per_map through segs_per_map when seg_off != NULL.
 template <typename T, bool SWAP, bool STEER>
 static int launch(const T* pts, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map,
@@ -306,17 +469,22 @@ static int launch(const T* pts, int64_t n_segs, const int64_t* seg_off, int64_t 
     int64_t dummy = 1;
     int rc = check_common(pts, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, &dummy);
     if (rc != PPNET_OK || dummy == 0) return rc;
-    constexpr int kSegChunk = kSegThreads * SegCfg<T>::kPerThread;
+    // more than one circle tile: later tiles continue from the verdict the earlier ones stored
+    PPNET_REQUIRE(verdict || omax <= kCircTile, "segcheck: verdict may only be null when omax <= 128");
     const int64_t per_map = segs_per_map > 0 ? segs_per_map : n_segs;
-    const int64_t chunks = (per_map + kSegChunk - 1) / kSegChunk;
-    PPNET_REQUIRE(chunks <= 65535, "segcheck: more than 65535*512 segments in one map");
+    // one CTA per map when there are enough maps to fill the machine (staging amortised over the whole map);
+    // otherwise cut maps into chunks until ~8 CTAs per SM exist
+    int64_t chunk = 8192;
+    while (chunk > kSegThreads && n_maps * ((per_map + chunk - 1) / chunk) < 8 * kNumSMs) chunk >>= 1;
+    const int64_t chunks = (per_map + chunk - 1) / chunk;
+    PPNET_REQUIRE(chunks <= 65535, "segcheck: more than 65535*8192 segments in one map");
     dim3 grid((unsigned)n_maps, (unsigned)chunks);
     if (dot_mode == PPNET_DOT_UNFUSED)
         segcheck_kernel<T, PPNET_DOT_UNFUSED, SWAP, STEER><<<grid, kSegThreads, 0, st>>>(
-            pts, seg_off, segs_per_map, obs, obs_cnt, omax, clearance, (T)bound, verdict, steer);
+            pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (T)bound, verdict, steer);
     else
         segcheck_kernel<T, PPNET_DOT_FUSED_SKX, SWAP, STEER><<<grid, kSegThreads, 0, st>>>(
-            pts, seg_off, segs_per_map, obs, obs_cnt, omax, clearance, (T)bound, verdict, steer);
+            pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (T)bound, verdict, steer);
     PPNET_LAUNCH_CHECK("segcheck_kernel");
     return PPNET_OK;
 }

@@ -236,7 +236,8 @@ def raster_circles_bits(obs, obs_cnt, resolution, inflate=0.0, out=None):
     return bits
 
 
-def dda_gridcheck(bits, resolution, segs_xy, seg_off=None, want_first=True, max_segs_per_map=None):
+def dda_gridcheck(bits, resolution, segs_xy, seg_off=None, want_first=True, max_segs_per_map=None, out=None,
+                  first_out=None):
     """Integer DDA vs bit-packed maps: bits i32[M,R,W], segs f32[N,4] grouped by map -> (verdict u8[N], first i32[N])."""
     _need(bits, torch.int32, "bits")
     _need(segs_xy, torch.float32, "segs_xy")
@@ -246,8 +247,10 @@ def dda_gridcheck(bits, resolution, segs_xy, seg_off=None, want_first=True, max_
     else:
         so = _need(seg_off, torch.int64, "seg_off")
         spm = max_segs_per_map if max_segs_per_map is not None else max(int((so[1:] - so[:-1]).max().item()), 1)
-    v = torch.empty(n, dtype=torch.uint8, device=bits.device)
-    fh = torch.empty(n, dtype=torch.int32, device=bits.device) if want_first else None
+    v = torch.empty(n, dtype=torch.uint8, device=bits.device) if out is None else _need(out, torch.uint8, "out")
+    fh = None
+    if want_first:
+        fh = torch.empty(n, dtype=torch.int32, device=bits.device) if first_out is None else _need(first_out, torch.int32, "first_out")
     check(lib().ppnet_dda_gridcheck(_ptr(bits), ctypes.c_int32(resolution), ctypes.c_int64(m), _ptr(segs_xy),
                                     ctypes.c_int64(n), _ptr(so), ctypes.c_int64(spm), _ptr(v), _ptr(fh), _stream()),
           "ppnet_dda_gridcheck")

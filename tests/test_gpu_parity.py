@@ -123,6 +123,81 @@ def test_segcheck_f32_vs_oracle_seeded(ops):
     assert np.array_equal(st.cpu().numpy(), want_st)
 
 
+def _margin_cases(rng, n, ftype):
+    """One circle per segment, placed so that the decision sits at a *relative* distance 10^U(-17,-2) from a
+    threshold of the fast path: |dis| vs thr, foot vs either end, |e-o| vs thr; plus degenerate / extreme
+    operands (zero and tiny segments, centre on an endpoint, tiny and huge radii, huge and non-finite coords)."""
+    scale = rng.choice([1.0, 1.0, 1.0, 1e-3, 1e3, 1e6], n)
+    s = rng.uniform(5, 219, (n, 2))
+    e = s + rng.normal(0, 30, (n, 2))
+    d = e - s
+    L = np.linalg.norm(d, axis=1)
+    nrm = np.stack([d[:, 1], -d[:, 0]], axis=1) / L[:, None]
+    thr = rng.uniform(2.3, 25, n)
+    pert = 10.0 ** rng.uniform(-17, -2, n) * rng.choice([-1, 1], n)
+    kind = rng.integers(0, 8, n)
+    t = rng.uniform(0.05, 0.95, n) * L                 # foot position along the segment
+    off = thr * rng.uniform(0.05, 0.95, n)             # lateral offset
+    # 0: |dis| ~ thr (foot inside)   1: foot ~ s   2: foot ~ e   3: |e-o| ~ thr   4: foot ~ s and |dis| ~ thr
+    off = np.where((kind == 0) | (kind == 4), thr * (1 + pert), off)
+    t = np.where((kind == 1) | (kind == 4), L * pert, t)
+    t = np.where(kind == 2, L * (1 + pert), t)
+    side = rng.choice([-1.0, 1.0], n)
+    o = s + d / L[:, None] * t[:, None] + nrm * (off * side)[:, None]
+    ang = rng.uniform(0, 2 * np.pi, n)
+    ov = e + np.stack([np.cos(ang), np.sin(ang)], axis=1) * (thr * (1 + pert))[:, None]
+    o = np.where((kind == 3)[:, None], ov, o)
+    # 5: centre exactly on s / e / the line   6, 7: random generic
+    on = rng.integers(0, 3, n)
+    o5 = np.where((on == 0)[:, None], s, np.where((on == 1)[:, None], e, s + d * rng.uniform(0, 1, (n, 1))))
+    o = np.where((kind == 5)[:, None], o5, o)
+    o = np.where((kind >= 6)[:, None], rng.uniform(0, 224, (n, 2)), o)
+    segs = np.concatenate([s, e], axis=1) * scale[:, None]
+    circ = np.concatenate([o * scale[:, None], ((thr - CLEAR / 2) * scale)[:, None]], axis=1)
+    # degenerate / extreme rows
+    idx = rng.permutation(n)[:n // 10]
+    for i in idx:
+        c = rng.integers(0, 8)
+        if c == 0: segs[i, 2:] = segs[i, :2]                                   # zero length
+        elif c == 1: segs[i, 2:] = segs[i, :2] + rng.normal(0, 1e-9, 2)        # tiny
+        elif c == 2: circ[i, 2] = -CLEAR / 2 + 10.0 ** rng.uniform(-14, -3)    # tiny thr
+        elif c == 3: circ[i, 2] = 10.0 ** rng.uniform(3, 30)                   # huge radius
+        elif c == 4: segs[i] *= 10.0 ** rng.uniform(8, 30)                     # huge coordinates (f32: may overflow to inf)
+        elif c == 5: segs[i, rng.integers(0, 4)] = rng.choice([np.nan, np.inf, -np.inf])
+        elif c == 6: circ[i, rng.integers(0, 3)] = rng.choice([np.nan, np.inf, -np.inf])
+        else: circ[i, :2] *= 10.0 ** rng.uniform(8, 30)
+    with np.errstate(over="ignore", invalid="ignore"):
+        return segs.astype(ftype), circ
+
+
+@pytest.mark.parametrize("flavour", ["f64_fused", "f64_unfused", "f32"])
+def test_segcheck_filter_margins_vs_oracle(ops, flavour):
+    """The division-free decisions and the bin culling must never change a verdict: 400 k pairs whose outcome
+    hinges on quantities within 1e-17..1e-2 (relative) of the fast path's thresholds, plus degenerate operands."""
+    rng = np.random.default_rng({"f64_fused": 1, "f64_unfused": 2, "f32": 3}[flavour])
+    n_maps, spm, omax = 25000, 16, 3
+    ftype = np.float32 if flavour == "f32" else np.float64
+    segs, circ = _margin_cases(rng, n_maps * spm, ftype)
+    # map m holds the circles of its first 3 segments: every segment meets its own circle (rows 0..2) or
+    # sharp circles built for a neighbour
+    obs = np.ascontiguousarray(circ.reshape(n_maps, spm, 3)[:, :omax])
+    cnt = rng.integers(0, omax + 1, n_maps).astype(np.int32)
+    cnt[: n_maps // 2] = omax
+    seg_map = np.repeat(np.arange(n_maps, dtype=np.int32), spm)
+    for bound in (224.0, 1e9):
+        if flavour == "f32":
+            v, st = ops.segcheck_mpnet_f32(dev(segs), dev(obs), dev(cnt), CLEAR, bound=bound, want_steer=True)
+            want, want_st = c_oracle.segcheck_f32(segs, seg_map, obs, cnt, CLEAR, bound=bound, threads=8)
+            assert np.array_equal(st.cpu().numpy(), want_st)
+        else:
+            mode = 0 if flavour == "f64_fused" else 1
+            v = ops.segcheck_edage_f64(dev(segs), dev(obs), dev(cnt), CLEAR, bound=bound, dot_mode=mode)
+            want = c_oracle.segcheck_f64(segs, seg_map, obs, cnt, CLEAR, bound=bound, dot_mode=mode, threads=8)
+        bad = np.nonzero(v.cpu().numpy() != want)[0]
+        assert len(bad) == 0, (flavour, bound, bad[:10], segs[bad[:3]], obs[seg_map[bad[:3]]])
+    assert 0.05 < want.mean() < 0.95
+
+
 def test_mpnet_feasible_and_lvc_golden(ops, golden):
     g = golden("segcheck_f32")
     args = (dev(g["path_pts"]), dev(g["path_off"]), dev(g["path_map"]), dev(g["obs"]), dev(g["obs_cnt"]),
