@@ -39,6 +39,8 @@ const char* ppnet_last_error(void);
 int ppnet_version(void);
 /* number of kernel launches this library has enqueued since load (bench.py's gpu_launches) */
 int64_t ppnet_launch_count(void);
+/* sizeof the parameter structs as compiled (0: ppnet_gen_params, 1: ppnet_path_params): layout guard for bindings */
+int64_t ppnet_sizeof_params(int32_t which);
 
 /* ---- A11  process_map.collision_check_circle_edge(s, e, obs, clearance)
  *      EDaGe-PP/process_map.py:383-425.  pts_rc[N][4] = (s_row, s_col, e_row, e_col) exactly as
@@ -175,6 +177,77 @@ typedef struct ppnet_gen_params {
     unsigned long long* counters;  /* [4] += maps_done, valid_paths, obstacles_accepted, tries    */
 } ppnet_gen_params;
 int ppnet_generate_maps(const ppnet_gen_params* params, void* stream);
+
+/* ---- A1 + A2 + A3 + A5 + A6 + A7 + A8 + A9: target-path synthesis, what PathGroup.generate does per accepted
+ *      Path (EDaGe-PP/PathGenerate.py:33-50 -> PathSeg.py:10-58, Path.py:78-98, 113-193, 224-356, 388-395,
+ *      463-537).  All pointers are device pointers; every output except space_raw is required.
+ *      S = seg_num, C = poly_order + 1, Np = 100 S, Nb = 100 S + 100.                                          */
+typedef struct ppnet_path_params {
+    int64_t path0, n_paths;        /* global path ids [path0, path0 + n_paths): the Philox unit                 */
+    int32_t seg_num, poly_order;   /* S <= 64, order 2..7 (reference: 10 and 4)                                 */
+    int32_t hmax, pomax;           /* hull / isle capacity (<= 128), path-obstacle capacity                     */
+    int32_t max_obst_iter;         /* A9 guard per isle (the reference loops until it succeeds)                 */
+    int32_t max_obst_rand;         /* row length of in_obst_rand                                                */
+    double clearance, map_size, resolution;
+    uint64_t seed;
+    /* optional caller-supplied draws (parity mode); NULL -> Philox keyed by the global path id                 */
+    const uint8_t* force_straight; /* [n]        PathGroup's 1 % forced-straight flag                           */
+    const uint8_t* in_straight;    /* [n][S]     resolved PathSeg.is_straight                                   */
+    const double* in_y;            /* [n][S][1000] np.random.random(1000) of PathSeg.random                     */
+    const double* in_uend;         /* [n][S]     np.random.random(1) of EndPoint (the end point itself with in_poly) */
+    const double* in_poly;         /* [n][S][C]  PathSeg.random(poly, endpoint): skip the fit                   */
+    const float* in_obst_rand;     /* [n][max_obst_rand] torch.rand(1) values consumed by set_obstacles         */
+    const int32_t* in_obst_rand_cnt; /* [n]                                                                     */
+    const int32_t* in_hull;        /* [n][hmax][2] raw hull cells in the reference's vertex order               */
+    const int32_t* in_hull_cnt;    /* [n]                                                                       */
+    /* A1 outputs */
+    double* poly;                  /* [n][S][C]  highest power first                                            */
+    double* endpoint;              /* [n][S]                                                                    */
+    uint8_t* is_straight;          /* [n][S]                                                                    */
+    uint8_t* path_straight;        /* [n]        Path.is_straight                                               */
+    double* seg_trans_local;       /* [n][S][2]  PathSeg.translation(): (EndPoint, polyval(EndPoint))           */
+    double* grad_st;               /* [n][S]                                                                    */
+    double* grad_end;              /* [n][S]                                                                    */
+    double* seg_length;            /* [n][S]                                                                    */
+    /* A2 outputs */
+    double* seg_rot;               /* [n][S]     PathSeg.Rotation after transform()                             */
+    double* seg_trans;             /* [n][S][2]  PathSeg.Translation after transform()                          */
+    double* segpoint_raw;          /* [n][S+1][2] Path.SegPoint (map units)                                     */
+    double* pathpoint_raw;         /* [n][Np][2] Path.PathPoint before normalisation                            */
+    double* length;                /* [n]        Path.Length                                                    */
+    int32_t* cells;                /* [n][Np][2] coord_euclidean2image(PathPoint, mapoffset = R)                */
+    /* A3 outputs */
+    double* up;                    /* [n][S][50][2] upboundary.point                                            */
+    double* up_dir;                /* [n][S][50][2] upboundary.direction (downboundary.direction = -up_dir)     */
+    double* down;                  /* [n][S][50][2] downboundary.point                                          */
+    double* cap_init;              /* [n][50][2] initboundary                                                   */
+    double* cap_end;               /* [n][50][2] endboundary                                                    */
+    double* boundary_raw;          /* [n][Nb][2] BoundaryPoint before normalisation                             */
+    /* A5: the rays path_space paints, in its order (init cap, end cap, up, down)                              */
+    double* ray_x0;                /* [n][Nb][2]                                                                */
+    double* ray_dir;               /* [n][Nb][2]                                                                */
+    double* step_num;              /* [n]        0.8 * clearance / step_len                                     */
+    uint8_t* space_raw;            /* [n][2R][2R] painted corridor (optional)                                   */
+    /* A6 */
+    int32_t* hull_raw;             /* [n][hmax][2]                                                              */
+    int32_t* hull_cnt;             /* [n]                                                                       */
+    /* A7 */
+    double* rotation;              /* [n]        Path.Rotation (degrees)                                        */
+    double* translation;           /* [n][2]     Path.Translation as stored (swapped)                           */
+    double* hull;                  /* [n][hmax][2] Path.ConvexHull                                              */
+    double* segpoint_img;          /* [n][S+1][2] Path.SegPointImage                                            */
+    double* pathpoint;             /* [n][Np][2] Path.PathPoint (row, col)                                      */
+    double* boundary;              /* [n][Nb][2] Path.BoundaryPoint                                             */
+    /* A8 */
+    int32_t* isle;                 /* [n][hmax][2] (lo, hi): isle = PathPoint[lo:hi]                            */
+    int32_t* isle_cnt;             /* [n]                                                                       */
+    /* A9 */
+    double* obs;                   /* [n][pomax][3] Path.obstacles [x, y, r]                                    */
+    int32_t* obs_cnt;              /* [n]                                                                       */
+    int32_t* obst_rand_used;       /* [n]        torch.rand(1) draws consumed                                   */
+    int32_t* status;               /* [n] bit0: max_obst_iter hit, bit1: supplied draws exhausted, bit2: pomax overflow */
+} ppnet_path_params;
+int ppnet_path_synthesize(const ppnet_path_params* params, void* stream);
 
 /* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
 int ppnet_ctx_create(int32_t device, void** ctx);

@@ -8,6 +8,7 @@ W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
 
 STREAM_PLACE, STREAM_OBST, STREAM_GMM_PARAM, STREAM_GMM_SAMPLE, STREAM_UNIFORM, STREAM_PATH = 1, 2, 3, 4, 5, 6
+STREAM_PATH_OBST = 7
 
 
 def philox4x32_10(key, ctr):
@@ -115,3 +116,27 @@ def gmm_sample(seed, sample0, n, mean, std, w):
     if D > 1:
         out[:, 1] = mean[comp, 1] + std[comp, 1] * z1
     return out, comp.astype(np.int32)
+
+
+def path_draws(seed, g, seg_num):
+    """A1 draws of path g (ppnet_b200/csrc/path_synth.cu): block 0 (x,y) -> forced-straight draw; piece i: block
+    1 + 502 i: (x,y) -> is_straight draw, (z,w) -> EndPoint draw; blocks 2 + 502 i + j (j < 500): y[2j], y[2j+1].
+    -> (forced bool, straight bool[S], y f64[S,1000], u_end f64[S])."""
+    key = key_of(seed)
+    r0 = philox4x32_10(key, _ctr([0], STREAM_PATH, g))
+    forced = not (u53(r0[0, 0], r0[0, 1]) > 0.01)
+    straight, ys, ue = [], [], []
+    for i in range(seg_num):
+        b0 = 1 + 502 * i
+        r = philox4x32_10(key, _ctr(b0 + np.arange(501), STREAM_PATH, g))
+        straight.append(forced or bool(u53(r[0, 0], r[0, 1]) < 0.2))
+        ue.append(float(u53(r[0, 2], r[0, 3])))
+        ys.append(np.stack([u53(r[1:, 0], r[1:, 1]), u53(r[1:, 2], r[1:, 3])], axis=1).reshape(-1))
+    return forced, np.asarray(straight), np.asarray(ys), np.asarray(ue)
+
+
+def path_obst_draws(seed, g, n):
+    """A9 draws of path g: draw t = u24 of word (t & 3) of block (t >> 2), STREAM_PATH_OBST."""
+    nb = (n + 3) // 4
+    r = philox4x32_10(key_of(seed), _ctr(np.arange(nb), STREAM_PATH_OBST, g))
+    return u24(r.reshape(-1))[:n]

@@ -538,6 +538,174 @@ def corridor_rays(bnd, end_point, map_size, resolution):
 
 
 # --------------------------------------------------------------------------------------------
+# A7  Path.space_normalization, point part (EDaGe-PP/Path.py:157-193)
+# --------------------------------------------------------------------------------------------
+def space_normalization_points(seg_point, path_point, boundary_point, hull_raw, map_size, resolution):
+    """Given the raw (map-unit) SegPoint/PathPoint/BoundaryPoint and the raw integer hull (cells at offset R):
+    Rotation = atan(Ey/Ex)/pi*180 - 135 (:159; `atan`, not atan2); hull rotated about (R, R) by -Rotation and
+    shifted so that its vertex mean sits at (R/2, R/2) (:162-176); every point set goes rotate -> A4 rounding
+    (offset R) -> + the same shift (:180-188).  Returns dict(Rotation, Translation (as stored: swapped),
+    ConvexHull, SegPointImage, PathPoint, BoundaryPoint)."""
+    R = f64(resolution)
+    seg_point = np.asarray(seg_point, dtype=np.float64)
+    e = seg_point[-1]
+    rotation = math.atan(e[1] / e[0]) / np.pi * 180 + (-135)
+    rad = -rotation / 180 * np.pi
+    c, s = np.cos(rad), np.sin(rad)
+    hull = np.asarray(hull_raw, dtype=np.float64) - R
+    hr = np.empty_like(hull)
+    for i, h in enumerate(hull):
+        hr[i] = rot2(c, s, h[0], h[1])
+    hr = hr + R
+    center = hr.mean(axis=0)
+    shift = np.array([R / 2, R / 2]) - center                   # [translation[1], translation[0]] of the stored value
+
+    def norm(pts):
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+        out = np.empty_like(pts)
+        for i, q in enumerate(pts):
+            out[i] = rot2(c, s, q[0], q[1])
+        return grid_index_vec(out, map_size, resolution, R).astype(np.float64) + shift
+
+    return dict(Rotation=rotation, Translation=np.array([shift[1], shift[0]]), ConvexHull=hr + shift,
+                SegPointImage=norm(seg_point), PathPoint=norm(path_point), BoundaryPoint=norm(boundary_point))
+
+
+# --------------------------------------------------------------------------------------------
+# A8  Path.search_isle (EDaGe-PP/Path.py:502-537)
+# --------------------------------------------------------------------------------------------
+def search_isle(path_point, hull, clearance, map_size, resolution, width_coef=0.2):
+    """-> list of (lo, hi): the isle is path_point[lo:hi].  For every hull edge longer than 5/step: nearest path
+    point (first minimum) to each end; the slice between them is an isle iff the first point whose distance to
+    the chord normal exceeds int(round(c/step*width_coef)) differs (coordinate-wise) from the slice's last point."""
+    pp = np.asarray(path_point, dtype=np.float64)
+    hull = np.asarray(hull, dtype=np.float64)
+    step_len = 1 / f64(resolution) * f64(map_size)
+    thr = int(np.round(f64(clearance) / step_len * width_coef))
+    H = len(hull)
+    out = []
+    for i in range(H):
+        j = 0 if i == H - 1 else i + 1
+        dv = hull[j] - hull[i]
+        if not np.sqrt(dot2_f64(dv[0], dv[1], dv[0], dv[1], DOT_FUSED_SKX)) > 5 / step_len:
+            continue
+        d0 = pp - hull[i]
+        d1 = pp - hull[j]
+        # np.linalg.norm = sqrt(ddot(x, x)) (fused on SkylakeX); compared by strict <: first minimum
+        n0 = np.sqrt([dot2_f64(v[0], v[1], v[0], v[1], DOT_FUSED_SKX) for v in d0])
+        n1 = np.sqrt([dot2_f64(v[0], v[1], v[0], v[1], DOT_FUSED_SKX) for v in d1])
+        i0, i1 = int(np.argmin(n0)), int(np.argmin(n1))
+        lo, hi = min(i0, i1), max(i0, i1)
+        b = pp[lo:hi]
+        if len(b) == 0:
+            continue                                             # (the reference would raise IndexError)
+        v = b[0] - b[-1]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            v = v / np.sqrt(dot2_f64(v[0], v[1], v[0], v[1], DOT_FUSED_SKX))
+        nrm = np.array([v[1], -v[0]])
+        p = b[-1]
+        for q in b:
+            w = q - b[0]
+            dis = abs(dot2_f64(w[0], w[1], nrm[0], nrm[1], DOT_FUSED_SKX))
+            if dis > thr:                                        # NaN never breaks
+                p = q
+                break
+        if (p != b[-1]).any():
+            out.append((lo, hi))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# A9  Path.set_obstacles (EDaGe-PP/Path.py:463-500) given the torch.rand(1) draws it consumes
+# --------------------------------------------------------------------------------------------
+def set_obstacles(path_point, isles, clearance, map_size, resolution, draws, max_iter=100000):
+    """path_point f64[Np,2] (normalised), isles = list of (lo, hi), draws = iterator of torch.rand(1) values
+    (float32-valued).  Returns (obstacles [[x, y, r], ...], number of draws used).  float32 where the
+    reference computes on float32 tensors (radius, motion, their sums), float64 elsewhere."""
+    pp = np.asarray(path_point, dtype=np.float64)
+    odd = pp[1::2]
+    c_px = f64(clearance) / f64(map_size) * f64(resolution)
+    size_clearance = c_px * 1.1
+    draws = list(draws)
+    used = 0
+
+    def rand():
+        nonlocal used
+        v = f32(draws[used])
+        used += 1
+        return v
+
+    obstacles = []
+    for lo, hi in isles:
+        isle = pp[lo:hi]
+        center = (isle[0] + isle[-1]) / 2
+        v = isle[0] - isle[-1]
+        dt = v / np.sqrt(dot2_f64(v[0], v[1], v[0], v[1], DOT_FUSED_SKX))
+        dn = np.array([dt[1], -dt[0]])
+        w = isle[int(len(isle) / 2)] - center
+        if not dot2_f64(w[0], w[1], dn[0], dn[1], DOT_FUSED_SKX) < 0:
+            dn = -dn
+        dis = []
+        for q in isle:
+            w = q - isle[0]
+            dis.append(abs(dot2_f64(w[0], w[1], dn[0], dn[1], DOT_FUSED_SKX)))
+        size_max = max(dis) * 2
+        peak = isle[dis.index(max(dis))]
+        obs_size = []                                            # float32 motions
+        size_pre = f32(0)
+        coord = None
+        it = 0
+        while (sum(obs_size, f32(0)) if obs_size else 0) < size_max:
+            it += 1
+            if it > max_iter:
+                break
+            first = len(obs_size) == 0
+            radius = f32(f32(rand() * f32(size_max)) / f32(2))               # torch.rand(1) * size_max / 2
+            random_normal = f32(1) if first else rand()
+            motion = f32(random_normal * f32(f32(radius + f32(size_pre)) + (f32(size_clearance) if first else f32(0))))
+            alt = f32(radius - (sum(obs_size, f32(0)) if obs_size else f32(0)))
+            if alt > motion:                                     # Python max(motion, alt): alt only if strictly greater
+                motion = alt
+            base = peak if first else coord
+            coord = base + f64(motion) * dn
+            if not first:
+                k = f32(f32(f32(f32(rand() - f32(0.5)) / f32(0.5)) * radius) / f32(2))
+                coord = coord + f64(k) * dt
+            dd = odd - coord
+            m = float(np.sqrt(dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]).min())
+            r_out = radius
+            if m < f64(f32(radius + f32(c_px))):
+                r_out = f64(m) - c_px
+            if r_out > 0:
+                obs_size.append(motion)
+                size_pre = r_out
+                obstacles.append([float(coord[1]), float(coord[0]), float(r_out)])
+    return obstacles, used
+
+
+# --------------------------------------------------------------------------------------------
+# PathGroup.generate's per-path work end to end (PathGenerate.py:33-50), given every random draw
+# --------------------------------------------------------------------------------------------
+def synthesize_path(y_noise, u_end, straight, clearance, map_size, resolution, obst_draws, path_straight=False,
+                    hull_raw=None, polyorder=4):
+    """y_noise f64[S,1000], u_end f64[S], straight bool[S], obst_draws = torch.rand(1) values for set_obstacles.
+    Returns a dict with every intermediate (names as in `ppnet_path_params`)."""
+    S = len(u_end)
+    segs = [pathseg_from_draws(y_noise[i], u_end[i], polyorder, bool(straight[i])) for i in range(S)]
+    chain = path_chain(segs)
+    bnd = draw_boundary(segs, chain, clearance)
+    x0, dr = corridor_rays(bnd, chain["SegPoint"][-1], map_size, resolution)
+    cells = grid_index_vec(chain["PathPoint"], map_size, resolution, resolution)
+    hr = np.asarray(hull2d(cells)) if hull_raw is None else np.asarray(hull_raw)
+    nrm = space_normalization_points(chain["SegPoint"], chain["PathPoint"], bnd["BoundaryPoint"], hr, map_size, resolution)
+    isles = [] if path_straight else search_isle(nrm["PathPoint"], nrm["ConvexHull"], clearance, map_size, resolution)
+    obs, used = set_obstacles(nrm["PathPoint"], isles, clearance, map_size, resolution, obst_draws, max_iter=256)
+    step_len = 1 / f64(resolution) * f64(map_size)
+    return dict(segs=segs, chain=chain, bnd=bnd, ray_x0=x0, ray_dir=dr, step_num=0.8 * f64(clearance) / step_len,
+                cells=cells, hull_raw=hr, norm=nrm, isles=isles, obstacles=np.asarray(obs).reshape(-1, 3), used=used)
+
+
+# --------------------------------------------------------------------------------------------
 # A16  process_map.add_init_end_single (EDaGe-PP/process_map.py:119-145)
 # --------------------------------------------------------------------------------------------
 def add_init_end_single(image, init, end):

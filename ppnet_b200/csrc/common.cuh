@@ -114,7 +114,8 @@ enum : uint32_t {
     STREAM_GMM_PARAM = 3,  // GMM parameters
     STREAM_GMM_SAMPLE = 4, // GMM samples
     STREAM_UNIFORM = 5,    // ppnet_uniform_f64
-    STREAM_PATH = 6,       // path synthesis draws
+    STREAM_PATH = 6,       // path synthesis draws (A1)
+    STREAM_PATH_OBST = 7,  // set_obstacles draws (A9)
 };
 
 }  // namespace ppnet

@@ -346,3 +346,111 @@ def generate_maps(bank, map0, n_maps, reps, obstacles_num, resolution=224, map_s
     p.counters = out.counters.data_ptr()
     check(lib().ppnet_generate_maps(ctypes.byref(p), _stream()), "ppnet_generate_maps")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# target-path synthesis (A1-A3, A5-A9)
+_PATH_FIELDS = [
+    ("path0", ctypes.c_int64), ("n_paths", ctypes.c_int64),
+    ("seg_num", ctypes.c_int32), ("poly_order", ctypes.c_int32), ("hmax", ctypes.c_int32), ("pomax", ctypes.c_int32),
+    ("max_obst_iter", ctypes.c_int32), ("max_obst_rand", ctypes.c_int32),
+    ("clearance", ctypes.c_double), ("map_size", ctypes.c_double), ("resolution", ctypes.c_double),
+    ("seed", ctypes.c_uint64),
+]
+_PATH_INPUTS = ["force_straight", "in_straight", "in_y", "in_uend", "in_poly", "in_obst_rand", "in_obst_rand_cnt", "in_hull",
+                "in_hull_cnt"]
+# name, dtype, shape as a function of dims d = dict(n, S, C, Np, Nb, h, po, R)
+_PATH_OUTPUTS = [
+    ("poly", torch.float64, lambda d: [d["n"], d["S"], d["C"]]),
+    ("endpoint", torch.float64, lambda d: [d["n"], d["S"]]),
+    ("is_straight", torch.uint8, lambda d: [d["n"], d["S"]]),
+    ("path_straight", torch.uint8, lambda d: [d["n"]]),
+    ("seg_trans_local", torch.float64, lambda d: [d["n"], d["S"], 2]),
+    ("grad_st", torch.float64, lambda d: [d["n"], d["S"]]),
+    ("grad_end", torch.float64, lambda d: [d["n"], d["S"]]),
+    ("seg_length", torch.float64, lambda d: [d["n"], d["S"]]),
+    ("seg_rot", torch.float64, lambda d: [d["n"], d["S"]]),
+    ("seg_trans", torch.float64, lambda d: [d["n"], d["S"], 2]),
+    ("segpoint_raw", torch.float64, lambda d: [d["n"], d["S"] + 1, 2]),
+    ("pathpoint_raw", torch.float64, lambda d: [d["n"], d["Np"], 2]),
+    ("length", torch.float64, lambda d: [d["n"]]),
+    ("cells", torch.int32, lambda d: [d["n"], d["Np"], 2]),
+    ("up", torch.float64, lambda d: [d["n"], d["S"], 50, 2]),
+    ("up_dir", torch.float64, lambda d: [d["n"], d["S"], 50, 2]),
+    ("down", torch.float64, lambda d: [d["n"], d["S"], 50, 2]),
+    ("cap_init", torch.float64, lambda d: [d["n"], 50, 2]),
+    ("cap_end", torch.float64, lambda d: [d["n"], 50, 2]),
+    ("boundary_raw", torch.float64, lambda d: [d["n"], d["Nb"], 2]),
+    ("ray_x0", torch.float64, lambda d: [d["n"], d["Nb"], 2]),
+    ("ray_dir", torch.float64, lambda d: [d["n"], d["Nb"], 2]),
+    ("step_num", torch.float64, lambda d: [d["n"]]),
+    ("space_raw", torch.uint8, lambda d: [d["n"], 2 * d["R"], 2 * d["R"]]),
+    ("hull_raw", torch.int32, lambda d: [d["n"], d["h"], 2]),
+    ("hull_cnt", torch.int32, lambda d: [d["n"]]),
+    ("rotation", torch.float64, lambda d: [d["n"]]),
+    ("translation", torch.float64, lambda d: [d["n"], 2]),
+    ("hull", torch.float64, lambda d: [d["n"], d["h"], 2]),
+    ("segpoint_img", torch.float64, lambda d: [d["n"], d["S"] + 1, 2]),
+    ("pathpoint", torch.float64, lambda d: [d["n"], d["Np"], 2]),
+    ("boundary", torch.float64, lambda d: [d["n"], d["Nb"], 2]),
+    ("isle", torch.int32, lambda d: [d["n"], d["h"], 2]),
+    ("isle_cnt", torch.int32, lambda d: [d["n"]]),
+    ("obs", torch.float64, lambda d: [d["n"], d["po"], 3]),
+    ("obs_cnt", torch.int32, lambda d: [d["n"]]),
+    ("obst_rand_used", torch.int32, lambda d: [d["n"]]),
+    ("status", torch.int32, lambda d: [d["n"]]),
+]
+
+
+class PathParams(ctypes.Structure):
+    """Mirror of `ppnet_path_params` (include/ppnet_b200.h)."""
+    _fields_ = (_PATH_FIELDS + [(k, ctypes.c_void_p) for k in _PATH_INPUTS] +
+                [(k, ctypes.c_void_p) for k, _, _ in _PATH_OUTPUTS])
+
+
+class PathBatch:
+    """Outputs of one path_synthesize launch (device tensors, one attribute per `ppnet_path_params` output)."""
+
+    def to_bank(self):
+        """The target-path bank generate_maps consumes (PathPoint, SegPointImage, ConvexHull, obstacles)."""
+        return PathBank(self.pathpoint, self.segpoint_img, self.hull, self.hull_cnt, self.obs, self.obs_cnt,
+                        length=self.length)
+
+
+def path_synthesize(path0, n_paths, seg_num=10, poly_order=4, clearance=1.0, map_size=50.0, resolution=224,
+                    seed=DEFAULT_SEED, hmax=64, pomax=32, max_obst_iter=256, want_space=False, device="cuda",
+                    force_straight=None, in_straight=None, in_y=None, in_uend=None, in_poly=None, in_obst_rand=None,
+                    in_obst_rand_cnt=None, in_hull=None, in_hull_cnt=None):
+    """PathGroup.generate's per-path work for global path ids [path0, path0 + n_paths)
+    (EDaGe-PP/PathGenerate.py:33-50): PathSeg.random x S -> Path.generate -> draw_boundary -> path_space rays
+    (+ paint) -> convexhull -> space_normalization (points) -> search_isle -> set_obstacles.
+    Deterministic in (seed, path id)."""
+    R = int(resolution)
+    S, C = int(seg_num), int(poly_order) + 1
+    dims = dict(n=n_paths, S=S, C=C, Np=100 * S, Nb=100 * S + 100, h=hmax, po=pomax, R=R)
+    out = PathBatch()
+    p = PathParams()
+    p.path0, p.n_paths, p.seg_num, p.poly_order, p.hmax, p.pomax = path0, n_paths, S, int(poly_order), hmax, pomax
+    p.max_obst_iter, p.clearance, p.map_size, p.resolution = max_obst_iter, float(clearance), float(map_size), float(R)
+    p.seed = seed
+    ins = dict(force_straight=(force_straight, torch.uint8), in_straight=(in_straight, torch.uint8),
+               in_y=(in_y, torch.float64), in_uend=(in_uend, torch.float64), in_poly=(in_poly, torch.float64),
+               in_obst_rand=(in_obst_rand, torch.float32), in_obst_rand_cnt=(in_obst_rand_cnt, torch.int32),
+               in_hull=(in_hull, torch.int32), in_hull_cnt=(in_hull_cnt, torch.int32))
+    for name, (t, dt) in ins.items():
+        if t is not None:
+            _need(t, dt, name)
+            setattr(p, name, t.data_ptr())
+    p.max_obst_rand = in_obst_rand.shape[1] if in_obst_rand is not None else 0
+    if in_hull is not None and in_hull.shape[1] != hmax:
+        raise PPNetError("in_hull must be [n, hmax, 2]")
+    for name, dt, shp in _PATH_OUTPUTS:
+        if name == "space_raw" and not want_space:
+            setattr(out, name, None)
+            continue
+        t = torch.zeros(shp(dims), dtype=dt, device=device)
+        setattr(out, name, t)
+        setattr(p, name, t.data_ptr())
+    check(lib().ppnet_path_synthesize(ctypes.byref(p), _stream()), "ppnet_path_synthesize")
+    out.n_paths, out.path0 = n_paths, path0
+    return out

@@ -312,7 +312,27 @@ def build_paths(n_paths, seed, clearance, seg_num=10):
             captured["down"] = np.asarray(path.Boundary.downboundary.point).copy()
             captured["init"] = np.asarray(path.Boundary.initboundary).copy()
             captured["end"] = np.asarray(path.Boundary.endboundary).copy()
-            ok = path.path_obstacles(resolution=224, map_size=50, map_offset=112)
+            # A8 / A9 capture: the isles search_isle returns and the torch.rand(1) values set_obstacles consumes
+            orig_isle, orig_rand = path.search_isle, torch.rand
+            rand_log = []
+
+            def spy_isle(*a, _o=orig_isle, _c=captured, **k):
+                isles = _o(*a, **k)
+                _c["isles"] = [np.asarray(b, dtype=np.float64).copy() for b in isles]
+                return isles
+
+            def spy_rand(*a, _o=orig_rand, **k):
+                v = _o(*a, **k)
+                rand_log.append(float(v.reshape(-1)[0]))
+                return v
+
+            path.search_isle = spy_isle
+            torch.rand = spy_rand
+            try:
+                ok = path.path_obstacles(resolution=224, map_size=50, map_offset=112)
+            finally:
+                torch.rand = orig_rand
+            captured["rand"] = np.asarray(rand_log, dtype=np.float64)
         if not ok:
             continue
         recs.append(dict(path=path, straight=np.asarray(draws_straight), y=np.asarray(draws_y),
@@ -356,6 +376,10 @@ def gen_paths():
             out[pre + "Space"] = (p.Space[0].cpu().numpy() * 255).round().astype(np.uint8)
             obs = [[float(o[0]), float(o[1]), float(o[2])] for o in p.obstacles]
             out[pre + "obstacles"] = np.asarray(obs, dtype=np.float64).reshape(-1, 3)
+            isles = cap.get("isles", [])
+            out[pre + "isle_off"] = np.cumsum([0] + [len(b) for b in isles]).astype(np.int64)
+            out[pre + "isle_pts"] = (np.concatenate(isles, axis=0) if isles else np.zeros([0, 2])).astype(np.float64)
+            out[pre + "obst_rand"] = cap["rand"]
             k += 1
     out["n_paths"] = k
     np.savez_compressed(os.path.join(HERE, "paths.npz"), **out)

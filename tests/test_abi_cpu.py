@@ -57,3 +57,12 @@ def test_ops_refuse_cpu_tensors():
     from ppnet_b200 import PPNetError, ops
     with pytest.raises(PPNetError):
         ops.grid_index_f64(torch.zeros(4, 2, dtype=torch.float64), 50, 224, 112)
+
+
+def test_parameter_struct_layouts_match_the_library():
+    import ctypes
+    from ppnet_b200 import _lib, ops
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    L.ppnet_sizeof_params.restype = ctypes.c_int64
+    assert L.ppnet_sizeof_params(ctypes.c_int32(0)) == ctypes.sizeof(ops.GenParams)
+    assert L.ppnet_sizeof_params(ctypes.c_int32(1)) == ctypes.sizeof(ops.PathParams)

@@ -342,3 +342,30 @@ def test_raster_and_dda_python_vs_c():
         hit, k = orc.dda_gridcheck(bits[sm[i]], 224, segs[i, :2], segs[i, 2:])
         assert hit == bool(v[i]) and k == fh[i], i
     assert 0.2 < v.mean() < 0.99
+
+
+def test_space_normalization_isles_and_path_obstacles_vs_reference(golden):
+    """A7 (point part), A8 and A9 against the real Path.space_normalization / search_isle / set_obstacles
+    (A9 replays the torch.rand(1) values the reference consumed)."""
+    g = golden("paths")
+    for k in range(int(g["n_paths"])):
+        pre = "p%d_" % k
+        c = int(g[pre + "clearance"])
+        n = orc.space_normalization_points(g[pre + "SegPoint_raw"], g[pre + "PathPoint_raw"], g[pre + "BoundaryPoint_raw"],
+                                           g[pre + "hull_raw"], 50, 224)
+        assert abs(n["Rotation"] - float(g[pre + "Rotation"])) < 1e-12
+        for name in ("Translation", "ConvexHull", "SegPointImage", "PathPoint", "BoundaryPoint"):
+            np.testing.assert_allclose(n[name], g[pre + name], rtol=0, atol=1e-10, err_msg=name)
+        isles = orc.search_isle(g[pre + "PathPoint"], g[pre + "ConvexHull"], c, 50, 224)
+        off = g[pre + "isle_off"]
+        assert len(isles) == len(off) - 1
+        for (lo, hi), i in zip(isles, range(len(off) - 1)):
+            assert np.array_equal(g[pre + "PathPoint"][lo:hi], g[pre + "isle_pts"][off[i]:off[i + 1]])
+        obs, used = orc.set_obstacles(g[pre + "PathPoint"], isles, c, 50, 224, g[pre + "obst_rand"])
+        assert used == len(g[pre + "obst_rand"])
+        np.testing.assert_allclose(np.asarray(obs).reshape(-1, 3), g[pre + "obstacles"], rtol=1e-12, atol=0)
+        # the invariant A9 guarantees: every emitted circle keeps clearance c_px to all odd path points
+        odd = g[pre + "PathPoint"][1::2]
+        for x, y, r in obs:
+            d = np.sqrt((odd[:, 0] - y) ** 2 + (odd[:, 1] - x) ** 2).min()
+            assert d >= r + c / 50 * 224 - 1e-4          # radius is float32 when it was not clamped
