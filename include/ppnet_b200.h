@@ -95,6 +95,12 @@ int ppnet_corridor_paint(const double* x0, const double* dir, const double* step
                          double mapoffset, int32_t W, int32_t H, uint8_t value, uint8_t* space,
                          void* stream);
 
+/* ---- A7 (mask) / N1: torchvision's rigid resampling of a corridor mask: RandomRotation(degrees=(d, d)) (nearest,
+ *      about the image centre) then functional.affine(translate=(tx, ty)), cropped to the top-left Ro x Ro
+ *      (EDaGe-PP/Path.py:160-161, 175-178; MapGenerate.py:102-106).  src[n][Ws][Ws] -> out[n][Ro][Ro] uint8.      */
+int ppnet_mask_rigid(const uint8_t* src, int32_t Ws, const double* angle_deg, const double* translate, int64_t n,
+                     int32_t Ro, uint8_t* out, void* stream);
+
 /* ---- A6   Path.convexhull  EDaGe-PP/Path.py:388-395 (scipy.spatial.ConvexHull on integer cells)
  *      pts[P][np][2] int32 -> hull[P][hmax][2] CCW from the lexicographically smallest vertex,
  *      strict corners only; hull_cnt[P] (a value > hmax means the output was truncated).          */
@@ -130,6 +136,16 @@ int ppnet_gmm_sample(uint64_t seed, uint64_t sample0, int64_t n, int32_t order, 
 int ppnet_raster_circles_bits(const double* obs, const int32_t* obs_cnt, int32_t omax,
                               int64_t n_maps, int32_t resolution, double inflate, uint32_t* bits,
                               void* stream);
+
+/* ---- A15 return value + MapGenerate.py:111: image[M][3][R][R] float32, 1 = free / 0 = obstacle from the bit-packed
+ *      map, plus `add` (same shape, the placed corridor mask `path_space`; may be NULL).                         */
+int ppnet_bits_to_image(const uint32_t* bits, int32_t resolution, int64_t n_maps, const float* add, float* image,
+                        void* stream);
+
+/* ---- A16  process_map.add_init_end_single(image, init, end)  EDaGe-PP/process_map.py:119-145
+ *      image[M][3][R][R] float32 in place; init/end[M][2] (row, col): 7x7 (255, 0, 0) stamps, clipped.           */
+int ppnet_add_init_end(float* image, int32_t resolution, const double* init, const double* end, int64_t n_maps,
+                       void* stream);
 
 /* ---- integer DDA grid check (new functionality; endpoints snapped with the A4 rule).
  *      segs_xy[N][4] float32 pixel coordinates grouped by map (CSR: pass the longest row in
@@ -228,12 +244,14 @@ typedef struct ppnet_path_params {
     double* ray_dir;               /* [n][Nb][2]                                                                */
     double* step_num;              /* [n]        0.8 * clearance / step_len                                     */
     uint8_t* space_raw;            /* [n][2R][2R] painted corridor (optional)                                   */
+    uint8_t* space;                /* [n][R][R]  Path.Space: the corridor after space_normalization (with space_raw) */
     /* A6 */
     int32_t* hull_raw;             /* [n][hmax][2]                                                              */
     int32_t* hull_cnt;             /* [n]                                                                       */
     /* A7 */
     double* rotation;              /* [n]        Path.Rotation (degrees)                                        */
     double* translation;           /* [n][2]     Path.Translation as stored (swapped)                           */
+    double* neg_rotation_ws;       /* [n]        workspace (-rotation, the angle handed to the mask rotation)   */
     double* hull;                  /* [n][hmax][2] Path.ConvexHull                                              */
     double* segpoint_img;          /* [n][S+1][2] Path.SegPointImage                                            */
     double* pathpoint;             /* [n][Np][2] Path.PathPoint (row, col)                                      */

@@ -47,9 +47,47 @@ __global__ void corridor_paint_kernel(const double* __restrict__ x0, const doubl
     }
 }
 
+// A7 (mask part) / N1: the rigid resampling torchvision applies to a corridor mask -- T.RandomRotation(degrees=(d, d))
+// (nearest, about the image centre, fill 0) followed by T.functional.affine(translate=(tx, ty)) (nearest) and a crop
+// to the top-left Ro x Ro (Path.py:160-161, 175-178; MapGenerate.py:102-106).  Two nearest-neighbour passes, so
+// the two roundings are kept separate:  (i, j) -> (rint(i - ty), rint(j - tx)) -> rotate by d about (Ws-1)/2 -> rint.
+// Identical pixels to the reference on all golden corridors (float64 here, float32 grids there).
+__global__ void mask_rigid_kernel(const uint8_t* __restrict__ src, int Ws, const double* __restrict__ angle_deg,
+                                  const double* __restrict__ translate, int Ro, uint8_t* __restrict__ out) {
+    const int64_t m = blockIdx.y;
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= Ro * Ro) return;
+    const int i = px / Ro, j = px % Ro;
+    const double tx = translate[2 * m], ty = translate[2 * m + 1];
+    const double j2 = rint((double)j - tx), i2 = rint((double)i - ty);
+    uint8_t v = 0;
+    if (j2 >= 0.0 && j2 < (double)Ws && i2 >= 0.0 && i2 < (double)Ws) {
+        const double c = 0.5 * (double)(Ws - 1);
+        const double th = angle_deg[m] / 180.0 * 3.14159265358979323846;
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        const double x = j2 - c, y = i2 - c;
+        const double js = rint(cs * x - sn * y + c), is = rint(sn * x + cs * y + c);
+        if (js >= 0.0 && js < (double)Ws && is >= 0.0 && is < (double)Ws) v = src[((size_t)m * Ws + (int)is) * Ws + (int)js];
+    }
+    out[((size_t)m * Ro + i) * Ro + j] = v;
+}
+
 }  // namespace ppnet
 
 using namespace ppnet;
+
+extern "C" int ppnet_mask_rigid(const uint8_t* src, int32_t Ws, const double* angle_deg, const double* translate,
+                                int64_t n, int32_t Ro, uint8_t* out, void* stream) {
+    PPNET_REQUIRE(n >= 0 && Ws > 0 && Ro > 0, "mask_rigid: bad sizes");
+    if (n == 0) return PPNET_OK;
+    PPNET_REQUIRE(src && angle_deg && translate && out, "mask_rigid: null pointer");
+    PPNET_REQUIRE(n <= 65535, "mask_rigid: at most 65535 masks per launch");
+    dim3 grid((unsigned)((Ro * Ro + 255) / 256), (unsigned)n);
+    mask_rigid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, Ws, angle_deg, translate, Ro, out);
+    PPNET_LAUNCH_CHECK("mask_rigid_kernel");
+    return PPNET_OK;
+}
 
 extern "C" int ppnet_grid_index_f64(const double* pts, int64_t n_values, double map_size, double resolution,
                                     double mapoffset, int32_t* idx, void* stream) {

@@ -588,6 +588,11 @@ obstacles_kernel(ppnet_path_params P) {
     }
 }
 
+__global__ void neg_kernel(const double* __restrict__ a, double* __restrict__ b, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = -a[i];
+}
+
 }  // namespace ppnet
 
 using namespace ppnet;
@@ -606,7 +611,7 @@ extern "C" int ppnet_path_synthesize(const ppnet_path_params* pp_, void* stream)
                   P.seg_rot && P.seg_trans && P.segpoint_raw && P.pathpoint_raw && P.length && P.cells && P.up && P.up_dir &&
                   P.down && P.cap_init && P.cap_end && P.boundary_raw && P.ray_x0 && P.ray_dir && P.step_num && P.hull_raw &&
                   P.hull_cnt && P.rotation && P.translation && P.hull && P.segpoint_img && P.pathpoint && P.boundary &&
-                  P.isle && P.isle_cnt && P.obs && P.obs_cnt && P.obst_rand_used && P.status,
+                  P.isle && P.isle_cnt && P.obs && P.obs_cnt && P.obst_rand_used && P.status && P.neg_rotation_ws,
                   "path_synthesize: every output pointer except space_raw is required");
     PPNET_REQUIRE(!P.in_poly || P.in_uend, "path_synthesize: in_poly needs in_uend (= the end points)");
     PPNET_REQUIRE(!P.in_obst_rand || (P.in_obst_rand_cnt && P.max_obst_rand > 0), "path_synthesize: in_obst_rand needs counts");
@@ -640,6 +645,13 @@ extern "C" int ppnet_path_synthesize(const ppnet_path_params* pp_, void* stream)
     }
     normalize_kernel<<<(unsigned)P.n_paths, kChainThreads, 0, st>>>(P);
     PPNET_LAUNCH_CHECK("normalize_kernel");
+    if (P.space_raw && P.space) {                          // A7 mask: rotate by -Rotation, translate by Translation, crop R x R
+        neg_kernel<<<(unsigned)((P.n_paths + 127) / 128), 128, 0, st>>>(P.rotation, P.neg_rotation_ws, P.n_paths);
+        PPNET_LAUNCH_CHECK("neg_kernel");
+        int rc = ppnet_mask_rigid(P.space_raw, 2 * (int)P.resolution, P.neg_rotation_ws, P.translation, P.n_paths,
+                                  (int)P.resolution, P.space, stream);
+        if (rc != PPNET_OK) return rc;
+    }
     isle_kernel<<<(unsigned)P.n_paths, kIsleThreads, 0, st>>>(P);
     PPNET_LAUNCH_CHECK("isle_kernel");
     obstacles_kernel<<<(unsigned)((P.n_paths + 3) / 4), 128, 0, st>>>(P);

@@ -30,9 +30,69 @@ raster_kernel(const double* __restrict__ obs, const int32_t* __restrict__ obs_cn
     store_bitmap(bm, bits + (size_t)m * words, words);
 }
 
+// ------------------------------------------------------------------------------------------ compose
+// A15's return value + MapGenerate.py:111-113: map image f32[3][R][R], 1 = free (white), 0 = obstacle (black),
+// optionally + the placed corridor mask, then A16's two 7x7 red stamps.
+__global__ void bits_to_image_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restrict__ add,
+                                     float* __restrict__ img) {
+    const int64_t m = blockIdx.y;
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= R * R) return;
+    const int i = px / R, j = px % R;
+    const uint32_t w = bits[((size_t)m * R + i) * W + (j >> 5)];
+    float v = ((w >> (j & 31)) & 1u) ? 0.0f : 1.0f;
+    for (int ch = 0; ch < 3; ++ch) {
+        const size_t o = (((size_t)m * 3 + ch) * R + i) * R + j;
+        img[o] = add ? __fadd_rn(v, add[o]) : v;                       // map_img + path_space
+    }
+}
+
+// A16  process_map.add_init_end_single  EDaGe-PP/process_map.py:119-145: (255, 0, 0) on the cells
+// (round(p_r) + dj, round(p_c) + dk), dj, dk in -3..3, clipped to the image; round = half-to-even.
+__global__ void add_init_end_kernel(float* __restrict__ img, int R, const double* __restrict__ init,
+                                    const double* __restrict__ endp, int64_t n) {
+    const int64_t m = blockIdx.x;
+    if (m >= n) return;
+    const int t = threadIdx.x;                                         // 2 points x 49 cells
+    if (t >= 98) return;
+    const double* p = (t < 49 ? init : endp) + 2 * m;
+    const int c = t % 49, dj = c / 7 - 3, dk = c % 7 - 3;
+    const double r0 = rint(p[0]), r1 = rint(p[1]);
+    if (!(fabs(r0) < 1e9 && fabs(r1) < 1e9)) return;                   // NaN / huge: nothing lands in the image
+    const int i = (int)r0 + dj, j = (int)r1 + dk;
+    if (i < 0 || i >= R || j < 0 || j >= R) return;
+    float* base = img + (size_t)m * 3 * R * R + (size_t)i * R + j;
+    base[0] = 255.0f;
+    base[(size_t)R * R] = 0.0f;
+    base[(size_t)2 * R * R] = 0.0f;
+}
+
 }  // namespace ppnet
 
 using namespace ppnet;
+
+extern "C" int ppnet_bits_to_image(const uint32_t* bits, int32_t resolution, int64_t n_maps, const float* add,
+                                   float* image, void* stream) {
+    PPNET_REQUIRE(n_maps >= 0 && resolution > 0, "bits_to_image: bad sizes");
+    if (n_maps == 0) return PPNET_OK;
+    PPNET_REQUIRE(bits && image, "bits_to_image: null pointer");
+    PPNET_REQUIRE(n_maps <= 65535, "bits_to_image: at most 65535 maps per call");
+    const int W = (resolution + 31) / 32;
+    dim3 grid((unsigned)((resolution * resolution + 255) / 256), (unsigned)n_maps);
+    bits_to_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, resolution, W, add, image);
+    PPNET_LAUNCH_CHECK("bits_to_image_kernel");
+    return PPNET_OK;
+}
+
+extern "C" int ppnet_add_init_end(float* image, int32_t resolution, const double* init, const double* end,
+                                  int64_t n_maps, void* stream) {
+    PPNET_REQUIRE(n_maps >= 0 && resolution > 0, "add_init_end: bad sizes");
+    if (n_maps == 0) return PPNET_OK;
+    PPNET_REQUIRE(image && init && end, "add_init_end: null pointer");
+    add_init_end_kernel<<<(unsigned)n_maps, 128, 0, (cudaStream_t)stream>>>(image, resolution, init, end, n_maps);
+    PPNET_LAUNCH_CHECK("add_init_end_kernel");
+    return PPNET_OK;
+}
 
 extern "C" int ppnet_raster_circles_bits(const double* obs, const int32_t* obs_cnt, int32_t omax, int64_t n_maps,
                                          int32_t resolution, double inflate, uint32_t* bits, void* stream) {

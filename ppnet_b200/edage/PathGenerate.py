@@ -1,0 +1,51 @@
+"""EDaGe-PP/PathGenerate.py:20-50 -- PathGroup: `path_num` accepted target paths, one batched launch."""
+import numpy as np
+import torch
+
+from .. import ops
+from . import _state
+from .Path import Path, _dev
+
+ORDER = 4
+PATHSEGNUM = 10
+DIM = 2
+
+
+class PathGroup:
+    def __init__(self, path_num=5, resolution=224, map_size=50):
+        self.device = _dev()
+        self.Paths = []
+        self.TargetPaths = []
+        self.PathNum = path_num
+        self.Resolution = resolution
+        self.MapSize = map_size
+        self.MapOffset = self.Resolution / 2
+        self.SpacesObs = []
+        self.SpacesFree = []
+        self.Rotation = []
+        self.Translation = []
+        self.bank = None              # device-resident ops.PathBank (what MapGenerate.generate consumes)
+        self.batch = None
+
+    def generate(self, path_seg_num=3, poly_order=4, dim=2, clearance=1):
+        # the reference loops until path_num paths are accepted; path_obstacles() always accepts (Path.py:174 tests a
+        # tuple), so exactly path_num paths are drawn.  The 1 % forced-straight draw is part of each path's stream.
+        first = _state.next_path_ids(self.PathNum)
+        out = ops.path_synthesize(first, self.PathNum, seg_num=path_seg_num, poly_order=poly_order, clearance=clearance,
+                                  map_size=self.MapSize, resolution=self.Resolution, seed=_state.current_seed(),
+                                  want_space=True, device=self.device)
+        self.batch = out
+        self.bank = out.to_bank()
+        host = {k: v.cpu().numpy() for k, v in vars(out).items() if isinstance(v, torch.Tensor)}
+        for i in range(self.PathNum):
+            path = Path(seg_num=path_seg_num, poly_order=poly_order, dim=dim, clearance=clearance,
+                        is_straight=bool(host["path_straight"][i]))
+            path._id = first + i
+            path._run(self.Resolution, self.MapSize, batch=host, index=i)
+            path.generate(show_now=False)
+            path.draw_boundary(show_now=False)
+            rst = path.path_obstacles(resolution=self.Resolution, map_size=self.MapSize, map_offset=self.MapOffset)
+            if rst:
+                self.Paths.append(path)
+                self.TargetPaths.append(path)
+        return bool(np.size(self.TargetPaths))

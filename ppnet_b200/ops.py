@@ -385,10 +385,12 @@ _PATH_OUTPUTS = [
     ("ray_dir", torch.float64, lambda d: [d["n"], d["Nb"], 2]),
     ("step_num", torch.float64, lambda d: [d["n"]]),
     ("space_raw", torch.uint8, lambda d: [d["n"], 2 * d["R"], 2 * d["R"]]),
+    ("space", torch.uint8, lambda d: [d["n"], d["R"], d["R"]]),
     ("hull_raw", torch.int32, lambda d: [d["n"], d["h"], 2]),
     ("hull_cnt", torch.int32, lambda d: [d["n"]]),
     ("rotation", torch.float64, lambda d: [d["n"]]),
     ("translation", torch.float64, lambda d: [d["n"], 2]),
+    ("neg_rotation_ws", torch.float64, lambda d: [d["n"]]),
     ("hull", torch.float64, lambda d: [d["n"], d["h"], 2]),
     ("segpoint_img", torch.float64, lambda d: [d["n"], d["S"] + 1, 2]),
     ("pathpoint", torch.float64, lambda d: [d["n"], d["Np"], 2]),
@@ -445,7 +447,7 @@ def path_synthesize(path0, n_paths, seg_num=10, poly_order=4, clearance=1.0, map
     if in_hull is not None and in_hull.shape[1] != hmax:
         raise PPNetError("in_hull must be [n, hmax, 2]")
     for name, dt, shp in _PATH_OUTPUTS:
-        if name == "space_raw" and not want_space:
+        if name in ("space_raw", "space") and not want_space:
             setattr(out, name, None)
             continue
         t = torch.zeros(shp(dims), dtype=dt, device=device)
@@ -453,4 +455,41 @@ def path_synthesize(path0, n_paths, seg_num=10, poly_order=4, clearance=1.0, map
         setattr(p, name, t.data_ptr())
     check(lib().ppnet_path_synthesize(ctypes.byref(p), _stream()), "ppnet_path_synthesize")
     out.n_paths, out.path0 = n_paths, path0
+    return out
+
+
+def bits_to_image(bits, resolution, add=None):
+    """A15's return value: bits i32[M,R,W] -> image f32[M,3,R,R] (1 free / 0 obstacle), optionally + `add`."""
+    _need(bits, torch.int32, "bits")
+    m = bits.shape[0]
+    if add is not None:
+        _need(add, torch.float32, "add")
+    img = torch.empty([m, 3, resolution, resolution], dtype=torch.float32, device=bits.device)
+    check(lib().ppnet_bits_to_image(_ptr(bits), ctypes.c_int32(resolution), ctypes.c_int64(m), _ptr(add), _ptr(img),
+                                    _stream()), "ppnet_bits_to_image")
+    return img
+
+
+def add_init_end(image, init, end):
+    """A16 batched (EDaGe-PP/process_map.py:119-145): image f32[M,3,R,R] in place, init/end f64[M,2] (row, col)."""
+    _need(image, torch.float32, "image")
+    _need(init, torch.float64, "init")
+    _need(end, torch.float64, "end")
+    m, _, r, _ = image.shape
+    check(lib().ppnet_add_init_end(_ptr(image), ctypes.c_int32(r), _ptr(init), _ptr(end), ctypes.c_int64(m), _stream()),
+          "ppnet_add_init_end")
+    return image
+
+
+def mask_rigid(src, angle_deg, translate, out_size):
+    """torchvision's RandomRotation(degrees=(d, d)) + functional.affine(translate) + top-left crop on uint8 masks
+    (EDaGe-PP/Path.py:160-178, MapGenerate.py:102-106): src u8[n,Ws,Ws], angle_deg f64[n], translate f64[n,2] (tx, ty)
+    -> u8[n,out_size,out_size]."""
+    _need(src, torch.uint8, "src")
+    _need(angle_deg, torch.float64, "angle_deg")
+    _need(translate, torch.float64, "translate")
+    n, ws, _ = src.shape
+    out = torch.empty([n, out_size, out_size], dtype=torch.uint8, device=src.device)
+    check(lib().ppnet_mask_rigid(_ptr(src), ctypes.c_int32(ws), _ptr(angle_deg), _ptr(translate), ctypes.c_int64(n),
+                                 ctypes.c_int32(out_size), _ptr(out), _stream()), "ppnet_mask_rigid")
     return out

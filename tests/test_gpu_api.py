@@ -1,0 +1,173 @@
+"""GPU tests of the drop-in Python surface (ppnet_b200.edage.*, ppnet_b200.mpnet): the reference's own names and
+signatures, answered by the CUDA path.  Known-answer table: SURVEY.md 8(a) (values produced by the reference)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import ppnet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+C = 1 / 50 * 224
+
+# (s_xy, e_xy, circle or None, A12 verdict, A11 verdict)
+KAT = [
+    ((10, 10), (100, 10), (50, 14, 2), True, True),          # edge_hit
+    ((10, 10), (100, 10), (50, 14.3, 2), False, False),      # edge_miss
+    ((10, 10), (100, 10), (103, 10, 1), True, True),         # vertex_hit_e
+    ((10, 10), (100, 10), (8, 10, 3), False, False),         # start_inside_only: the start point is never vertex-tested
+    ((10, 10), (100, 10), (110, 10, 1), False, False),       # beyond_end_proj
+    ((10, 10), (100, 10), (50, 10, 1), True, True),          # on_line_center
+    ((-1, 10), (100, 10), None, True, False),                # oob x = -1: A11 tests row < 0 / col > 224
+    ((10, 225), (100, 10), None, True, False),               # oob y = 225
+    ((230, 10), (100, 10), None, False, True),               # x = 230: only A11 (col > 224)
+]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    assert torch.cuda.is_available(), "these tests need a B200"
+
+
+def test_known_answer_table_through_the_reference_signatures():
+    from ppnet_b200 import mpnet
+    from ppnet_b200.edage import process_map
+    mpnet.clearance = C
+    for s, e, circ, want12, want11 in KAT:
+        obs = [list(circ)] if circ else []
+        got11 = process_map.collision_check_circle_edge((s[1], s[0]), (e[1], e[0]), obs, C)       # (row, col) inputs
+        assert got11 == want11, ("A11", s, e, circ)
+        mpnet.obc = [obs]
+        got12 = mpnet.collision_check_circle_edge(torch.tensor(s, dtype=torch.float32), torch.tensor(e, dtype=torch.float32), 0)
+        assert got12 == want12, ("A12", s, e, circ)
+        assert mpnet.steerTo(np.float32(s), np.float32(e), 0) == (0 if want12 else 1)
+    # a whole path through the batched form == edge by edge
+    path = [[10.0, 10.0], [10.0, 100.0], [60.0, 150.0], [200.0, 150.0]]
+    obs = [[50, 14, 2], [150, 100, 9]]
+    v = process_map.collision_check_path(path, obs, C)
+    assert v.tolist() == [process_map.collision_check_circle_edge(path[i], path[i + 1], obs, C) for i in range(3)]
+
+
+def test_add_init_end_single_golden(golden):
+    from ppnet_b200.edage import process_map
+    g = golden("misc")
+    for i in range(len(g["init"])):
+        img = torch.from_numpy(g["img_in"][i].copy())
+        out = process_map.add_init_end_single(img, g["init"][i], g["end"][i])
+        assert out is img
+        assert np.array_equal(out.numpy(), g["img_out"][i])
+    dev_img = torch.from_numpy(g["img_in"][0].copy()).cuda()
+    process_map.add_init_end_single(dev_img, g["init"][0], g["end"][0])
+    assert np.array_equal(dev_img.cpu().numpy(), g["img_out"][0])
+
+
+def test_mpnet_module_api_vs_oracle(golden):
+    from ppnet_b200 import mpnet
+    g = golden("segcheck_f32")
+    mpnet.clearance = float(g["clearance"])
+    mpnet.obc = [g["obs"][m, :g["obs_cnt"][m]].tolist() for m in range(len(g["obs_cnt"]))]
+    po, lo = g["path_off"], g["lvc_off"]
+    for p in range(min(12, len(g["path_map"]))):
+        idx = int(g["path_map"][p])
+        path = [torch.from_numpy(w.copy()) for w in g["path_pts"][po[p]:po[p + 1]]]
+        assert mpnet.feasibility_check(path, idx) == int(g["feasible"][p])
+        out = mpnet.lvc(path, idx)
+        want = g["lvc_pts"][lo[p]:lo[p + 1]]
+        assert len(out) == len(want)
+        assert np.array_equal(np.stack([o.numpy() for o in out]), want)
+
+
+def test_gmm_mirror():
+    from ppnet_b200 import edage
+    from ppnet_b200.edage.GMM import GMM
+    edage.seed(3)
+    m = GMM(10, 2)
+    a = m.Distribution.sample([1000, ])
+    b = m.Distribution.sample([1000])
+    assert a.shape == (1000, 2) and a.is_cuda and a.dtype == torch.float32
+    assert not torch.equal(a, b)                                  # the stream moves on
+    edage.seed(3)
+    a2 = GMM(10, 2).Distribution.sample([1000, ])
+    assert torch.equal(a, a2)                                     # reproducible from the seed
+    assert m.Order == 10 and m.Dim == 2
+    assert float(a.min()) > -40 and float(a.max()) < 110         # means in [0, 70), std < 5
+
+
+def test_path_and_pathseg_mirrors():
+    from ppnet_b200 import edage
+    from ppnet_b200.edage.Path import Path, plot_obstacles
+    from ppnet_b200.edage.PathSeg import PathSeg
+    edage.seed(11)
+    seg = PathSeg(4, 2)
+    poly, end = seg.random()
+    assert poly.shape == (5,) and poly[-1] == 0 and 0 <= float(end[0]) <= 7
+    assert seg.gradient() == (seg.GradSt, seg.GradEnd)
+    ref = orc.pathseg_from_poly(poly, float(end[0]), seg.is_straight)
+    assert abs(float(seg.length()[0]) - ref["Length"]) <= 1e-9 * max(ref["Length"], 1)
+    p = Path(seg_num=10, poly_order=4, clearance=1, is_straight=False)
+    p.generate(show_now=False)
+    assert p.PathPoint.shape == (1000, 2) and p.SegPoint.shape == (11, 2) and len(p.PathSeg) == 10
+    p.draw_boundary(show_now=False)
+    assert p.BoundaryPoint.shape == (1100, 2)
+    assert p.path_obstacles(resolution=224, map_size=50, map_offset=112)
+    assert p.Space.shape == (3, 224, 224) and p.PathPoint.shape == (1000, 2)
+    hull = p.ConvexHull.numpy()
+    assert abs(hull.mean(axis=0) - 112).max() < 1e-6             # space_normalization centres the hull
+    ok, placed = p.boundary_check(0, [0, 0])
+    assert ok and np.allclose(placed, hull)
+    odd = p.PathPoint[1::2]
+    for x, y, r in p.obstacles:
+        assert np.sqrt((odd[:, 0] - y) ** 2 + (odd[:, 1] - x) ** 2).min() >= r + 4.48 - 1e-4
+    cells = p.coord_euclidean2image(np.array([[0.1, 0.2], [3.0, -4.0]]), 224)
+    assert np.array_equal(cells, orc.grid_index_vec(np.array([[0.1, 0.2], [3.0, -4.0]]), 50, 224, 224))
+    img = plot_obstacles((224, 224), [[50, 60, 10]], resolution=(224, 224))
+    assert img.shape == (3, 224, 224) and float(img[0, 60, 50]) == 0.0 and float(img[0, 5, 5]) == 1.0
+
+
+def test_mapgenerate_mirror_end_to_end(tmp_path):
+    from ppnet_b200 import edage
+    from ppnet_b200.edage import MapGenerate as MG
+    edage.seed(5)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        mg = MG.MapGenerate(path_num=3, resolution=224, map_size=50, obstacles_num=20, clearance=3)
+        mg.generate(map_num=18, folder_path=str(tmp_path), round_index=0)
+        P = 3
+        assert len(mg.MapLabel) == 18 and len(mg.PathGroup.TargetPaths) == P
+        lines = open("unsolved_problems.txt").read().strip().split("\n")
+        assert len(lines) == 18
+        c_px = 3 / 50 * 224
+        for g, ln in enumerate(lines):
+            prob = json.loads(ln)
+            label, angle, translation, segpoint, pathpoint = mg.MapLabel[g]
+            assert prob["Index"] == g and len(label) == 10 and pathpoint.shape == (1000, 2) and segpoint.shape == (11, 2)
+            assert np.allclose(prob["Init"], segpoint[0]) and np.allclose(prob["End"], segpoint[10])
+            j = (g // P) % P                                       # index rule MapGenerate.py:68
+            assert prob["Length"] == mg.PathGroup.TargetPaths[j].Length
+            # the label is the rigid placement of target path j (oracle A13)
+            want = orc.place_points(mg.PathGroup.TargetPaths[j].PathPoint, float(angle[0]), translation, 224)
+            assert np.abs(want - pathpoint).max() < 1e-7
+            odd = pathpoint[1::2]
+            for x, y, r in prob["Obstacles"]:
+                assert np.sqrt((odd[:, 0] - y) ** 2 + (odd[:, 1] - x) ** 2).min() > r + c_px - 1e-4
+            # the reference's own post-hoc checker accepts the label path against these obstacles (every 25th edge)
+            pts = pathpoint[::25]
+            seg_map = np.zeros(len(pts) - 1, dtype=np.int32)
+            segs = np.concatenate([pts[:-1], pts[1:]], axis=1)
+            obs = np.asarray(prob["Obstacles"], dtype=np.float64).reshape(1, -1, 3)
+            if obs.shape[1]:
+                v = c_oracle.segcheck_f64(segs, seg_map, obs, np.asarray([obs.shape[1]], dtype=np.int32), c_px)
+                assert not v.any()
+        imgs = mg.map_images(0, 4)
+        assert imgs.shape == (4, 3, 224, 224)
+        r0, c0 = (int(np.round(v)) for v in mg.MapLabel[0][3][0])
+        assert imgs[0, :, r0, c0].tolist() == [255.0, 0.0, 0.0]   # A16 stamp at the init point
+        one = mg.generate_map_randomly(mg.MapLabel[0][4], mg.MapLabel[0][3][0], mg.MapLabel[0][3][10], 1.0, [], 7)
+        assert one.shape == (3, 224, 224) and one.is_cuda
+    finally:
+        os.chdir(cwd)

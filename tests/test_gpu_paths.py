@@ -103,6 +103,8 @@ def test_path_synthesis_parity_mode_vs_reference(ops, golden, use_ref_hull):
             close(o["segpoint_img"][i], g[pre + "SegPointImage"], "SegPointImage", scale=224.0)
             close(o["pathpoint"][i], g[pre + "PathPoint"], "PathPoint", scale=224.0)
             close(o["boundary"][i], g[pre + "BoundaryPoint"], "BoundaryPoint", scale=224.0)
+            # A7 mask part: Path.Space after torchvision rotate + affine + crop, pixel for pixel
+            assert np.array_equal(o["space"][i], g[pre + "Space"]), "normalised corridor differs"
             if use_ref_hull:
                 close(o["hull"][i, :H], g[pre + "ConvexHull"], "ConvexHull", scale=224.0)
                 # A8: the same isles in the same order (the order follows the hull's vertex order)
