@@ -172,8 +172,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from ppnet_b200 import _lib, host, ops
-    from ppnet_b200.synthetic import synthetic_bank, synthetic_segments
+    from ppnet_b200 import _lib, host, ops, sharding
+    from ppnet_b200.synthetic import synthetic_segments
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -189,8 +189,14 @@ def run_ours(args):
     clear_px = CLEAR_UNITS / MAP_SIZE * R
 
     # ---- inputs (untimed): target-path bank, segments (host pinned + device), GMM parameters
-    bk = synthetic_bank(N_BANK, seed=0)
-    bank = ops.PathBank(*[torch.from_numpy(bk[k]).to(dev) for k in ("pathpt", "segpt", "hull", "hull_cnt", "obs", "obs_cnt")])
+    # target-path bank: PathGroup.generate on the device (A1-A9), N_BANK paths, identical on every rank
+    tb0 = time.perf_counter()
+    paths = ops.path_synthesize(0, N_BANK, seg_num=10, poly_order=4, clearance=CLEAR_UNITS, map_size=MAP_SIZE, resolution=R,
+                                seed=SEED, hmax=64, pomax=24, device=dev)
+    bank = paths.to_bank()
+    torch.cuda.synchronize()
+    bank_ms = 1e3 * (time.perf_counter() - tb0)
+    bk = {k: getattr(bank, k).cpu().numpy() for k in ("pathpt", "segpt", "hull", "hull_cnt", "obs", "obs_cnt")}
     segs64_h = torch.from_numpy(synthetic_segments(M, SEGS_PER_MAP, seed=100 + rank)).pin_memory()
     segs32_h = segs64_h.to(torch.float32).pin_memory()
     segs64, segs32 = segs64_h.to(dev), segs32_h.to(dev)
@@ -206,7 +212,7 @@ def run_ours(args):
     names = ["generate_maps", "segcheck_f64", "segcheck_f32", "dda_gridcheck", "gmm_sample"]
 
     def step(it, ev=None):
-        map0 = (it * world + rank) * M                       # every step generates NEW maps (global index range)
+        map0, _ = sharding.step_range(it, rank, world, M)   # every step generates NEW maps (global index range)
         if ev: ev[0].record()
         ops.generate_maps(bank, map0, M, REPS, O, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED, out=gen,
                           raster_inflate=clear_px / 2)
@@ -252,11 +258,9 @@ def run_ours(args):
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-        allc = [torch.zeros_like(counters) for _ in range(world)]
-        dist.all_gather(allc, counters)                      # the path's only collective: int64[4] per rank
-        tot = torch.stack(allc).sum(0).cpu().numpy()
-    else:
-        tot = counters.cpu().numpy()
+    # the path's only collective: one all_gather of int64[4] per rank
+    _, totals, _ = sharding.gather_counts(counters)
+    tot = np.asarray([totals[n] for n in sharding.COUNTER_NAMES])
     ms_step = ms_total / args.steps
     k_ms = np.asarray([[e[i].elapsed_time(e[i + 1]) for i in range(5)] for e in evs]).mean(axis=0)   # mean over the timed launches
     if os.environ.get("PPNET_BENCH_DEBUG"):
@@ -307,13 +311,15 @@ def run_ours(args):
         s64, s32 = segs64_h.numpy(), segs32_h.numpy()
         gm, gs, gw = g_mean.cpu().numpy(), g_std.cpu().numpy(), g_w.cpu().numpy()
 
+        checks = dict(segs_rc_f64=s64, segs_xy_f32=s32, clearance_px=clear_px, verdict_f64=hv64, verdict_f32=hv32,
+                      verdict_dda=hvd)
+
         def e2e_step(it):
-            map0 = (it * world + rank) * M
+            # one host call: upload this step's candidate segments, generate the maps, run the three verdict kernels
+            # against them, download labels / obstacle sets / bitmaps / verdicts (copies overlap kernels slice by slice)
+            map0, _ = sharding.step_range(it, rank, world, M)
             host.generate_maps_host(ctx, hbank, map0, M, REPS, O, hout, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED,
-                                    raster_inflate=clear_px / 2)
-            ctx.segcheck_edage_f64(s64, hout["obs"], hout["obs_cnt"], clear_px, out=hv64)
-            ctx.segcheck_mpnet_f32(s32, hout["obs"], hout["obs_cnt"], clear_px, out=hv32)
-            ctx.dda_gridcheck(hout["bits"], R, s32, out=hvd)
+                                    raster_inflate=clear_px / 2, checks=checks)
             ctx.gmm_sample(SEED, map0 * GMM_PER_MAP, n_gmm, gm, gs, gw, out=hgmm)
 
         e2e_steps = max(2, min(args.steps, 5))
@@ -323,7 +329,10 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for it in range(e2e_steps):
+            ta = time.perf_counter()
             e2e_step(100 + it)
+            if os.environ.get("PPNET_BENCH_DEBUG"):
+                print("e2e step %d: %.2f ms" % (it, 1e3 * (time.perf_counter() - ta)), file=sys.stderr)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         b1 = ctx.bytes_moved()
@@ -335,7 +344,8 @@ def run_ours(args):
         e2e = {"value": seg_per_step * e2e_steps / dt, "unit": "segments/s",
                "h2d_bytes_per_step": (b1[0] - b0[0]) // e2e_steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // e2e_steps,
                "ms_per_step": 1e3 * dt / e2e_steps, "valid_paths_per_s": M * world * e2e_steps / dt,
-               "timer": "host wall clock around synchronous host-API calls (each call synchronises before returning)"}
+               "timer": "host wall clock around synchronous host-API calls (each call synchronises before returning)",
+               "api": "ppnet_generate_and_check_host + ppnet_gmm_sample_host, pinned host buffers"}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -351,6 +361,7 @@ def run_ours(args):
                                        "target paths" % (M, SEGS_PER_MAP, GMM_PER_MAP, N_BANK),
                            "maps_per_gpu": M, "segments_per_step": seg_per_step, "parallelism": "map-sharded x%d" % world,
                            "l2": "inputs larger than L2 (segments 492 MB + labels 162 MB per step); no flush needed",
+                           "bank": "%d target paths synthesised on the device (A1-A9) in %.1f ms, untimed" % (N_BANK, bank_ms),
                            "placement_tries_per_map": tries / max(maps_done, 1),
                            "accepted_random_obstacles_per_map": acc_obs / max(maps_done, 1)},
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),

@@ -292,6 +292,21 @@ int ppnet_bank_free(void* bank);
 /* MapGenerate.generate with HOST outputs: `params` carries the settings and host out_* pointers
  * (its bank_* and in_* fields are ignored; counters, if set, is a host uint64[4] accumulator).    */
 int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* params);
+/* MapGenerate.generate + the verdicts on the freshly generated maps in ONE host call: slice by slice the candidate
+ * segments (uniform grouping, segs_per_map per map, HOST pointers) are uploaded, the maps generated, A11 / A12 / DDA
+ * run against them on the device, and labels + verdicts downloaded; uploads, kernels and downloads of neighbouring
+ * slices overlap.  NULL verdict pointers skip that check.                                                        */
+typedef struct ppnet_pipeline_io {
+    const double* segs_rc_f64;     /* [n_maps * segs_per_map][4] (s_row, s_col, e_row, e_col), for verdict_f64  */
+    const float* segs_xy_f32;      /* [n_maps * segs_per_map][4] (s_x, s_y, e_x, e_y), for verdict_f32 / _dda   */
+    int64_t segs_per_map;
+    double clearance_px, bound;
+    int32_t dot_mode, reserved;
+    uint8_t* verdict_f64;          /* A11 */
+    uint8_t* verdict_f32;          /* A12 */
+    uint8_t* verdict_dda;          /* integer DDA vs the bit-packed map */
+} ppnet_pipeline_io;
+int ppnet_generate_and_check_host(void* ctx, void* bank, const ppnet_gen_params* params, const ppnet_pipeline_io* io);
 int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t resolution, int64_t n_maps,
                              const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
                              int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit);

@@ -11,16 +11,19 @@
 
 namespace ppnet {
 
+constexpr int kSlotBufs = 12;
 struct Slot {
     cudaStream_t st = nullptr;
-    void* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    void* buf[kSlotBufs] = {};
+    size_t cap[kSlotBufs] = {};
 };
 
 struct Ctx {
     int device = 0;
     Slot slot[2];
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    unsigned long long* pinned_cnt = nullptr;    // pinned staging for per-slice counters: a device->host copy into
+    size_t pinned_cap = 0;                       // pageable memory would block the issuing thread and serialise slices
 };
 
 static int slot_reserve(Slot& s, int i, size_t bytes) {
@@ -133,9 +136,10 @@ extern "C" int ppnet_ctx_destroy(void* ctx) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return PPNET_OK;
     cudaSetDevice(c->device);
+    if (c->pinned_cnt) cudaFreeHost(c->pinned_cnt);
     for (int i = 0; i < 2; ++i) {
         if (c->slot[i].st) { cudaStreamSynchronize(c->slot[i].st); cudaStreamDestroy(c->slot[i].st); }
-        for (int j = 0; j < 6; ++j) if (c->slot[i].buf[j]) cudaFree(c->slot[i].buf[j]);
+        for (int j = 0; j < kSlotBufs; ++j) if (c->slot[i].buf[j]) cudaFree(c->slot[i].buf[j]);
     }
     delete c;
     return PPNET_OK;
@@ -263,28 +267,46 @@ extern "C" int ppnet_bank_free(void* bank) {
 }
 
 // `p` carries the generation settings and HOST output pointers (bank_* / in_* fields are ignored: the bank
-// comes from `bank`, draws from Philox).  Maps are produced in slices; slice k's device->host copies overlap
-// slice k+1's kernel.
-extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* p) {
-    Ctx* c = (Ctx*)ctx;
-    Bank* b = (Bank*)bank;
+// comes from `bank`, draws from Philox).  Maps are produced in slices on two streams: slice k's device->host
+// copies overlap slice k+1's host->device copies and kernels.  With `io`, every slice also uploads its candidate
+// segments and runs the verdict kernels against the maps it has just generated -- the obstacle sets and bitmaps
+// never leave the device in between (ppnet_generate_and_check_host).
+static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const ppnet_pipeline_io* io) {
     PPNET_REQUIRE(c && b && p, "generate_maps_host: null argument");
     PPNET_REQUIRE(p->n_maps >= 0, "generate_maps_host: negative n_maps");
     PPNET_REQUIRE(!p->in_angle && !p->in_trans && !p->in_cand, "generate_maps_host: caller-supplied draws need the device API");
+    const int64_t spm = io ? io->segs_per_map : 0;
+    if (io) {
+        PPNET_REQUIRE(spm > 0, "generate_and_check_host: segs_per_map must be positive");
+        PPNET_REQUIRE((io->verdict_f64 == nullptr) || io->segs_rc_f64, "generate_and_check_host: verdict_f64 needs segs_rc_f64");
+        PPNET_REQUIRE((io->verdict_f32 == nullptr && io->verdict_dda == nullptr) || io->segs_xy_f32,
+                      "generate_and_check_host: verdict_f32 / verdict_dda need segs_xy_f32");
+    }
     PPNET_CUDA(cudaSetDevice(c->device));
     const int R = (int)p->resolution, W = (R + 31) / 32;
     const int64_t O = p->obstacles_num, oo = O + b->pomax;
-    const int64_t kSlice = 2048;
-    // per-map byte sizes of the outputs, slot buffer ids: 0 pathpt, 1 segpt, 2 obs, 3 bits, 4 small ints, 5 counters
+    const int64_t kSlice = io ? 1024 : 2048;
+    // per-map byte sizes of the outputs, slot buffer ids: 0 pathpt, 1 segpt, 2 obs, 3 bits, 4 small ints, 5 counters,
+    // 6 segments f64, 7 segments f32, 8 / 9 / 10 verdicts
     const size_t b_pp = sizeof(double) * 2 * (size_t)b->np, b_sp = sizeof(double) * 2 * (size_t)b->nseg1;
     const size_t b_ob = sizeof(double) * 3 * (size_t)oo, b_bt = (size_t)R * W * 4;
     const size_t b_small = 8 /*angle*/ + 8 /*trans*/ + 4 * 3 /*obs_cnt, rand_cnt, tries*/ + 4 /*valid, padded*/;
     const int64_t n_slices = (p->n_maps + kSlice - 1) / kSlice;
-    std::vector<unsigned long long> cnt_keep(4 * (size_t)std::max<int64_t>(n_slices, 1), 0ull);
+    const size_t cnt_words = 4 * (size_t)std::max<int64_t>(n_slices, 1);
+    if (c->pinned_cap < cnt_words) {
+        if (c->pinned_cnt) cudaFreeHost(c->pinned_cnt);
+        c->pinned_cnt = nullptr; c->pinned_cap = 0;
+        PPNET_CUDA(cudaHostAlloc((void**)&c->pinned_cnt, sizeof(unsigned long long) * (cnt_words + 64), cudaHostAllocDefault));
+        c->pinned_cap = cnt_words + 64;
+    }
+    unsigned long long* cnt_keep = c->pinned_cnt;
+    for (size_t i = 0; i < cnt_words; ++i) cnt_keep[i] = 0ull;
+    const bool need_bits = p->out_bits || (io && io->verdict_dda);
     int k = 0;
     for (int64_t m0 = 0; m0 < p->n_maps; m0 += kSlice, ++k) {
         Slot& s = c->slot[k & 1];
         const int64_t nm = std::min(kSlice, p->n_maps - m0);
+        const int64_t ns = nm * spm;
         int rc;
         if ((rc = slot_reserve(s, 0, b_pp * nm)) != PPNET_OK) return rc;
         if ((rc = slot_reserve(s, 1, b_sp * nm + 16)) != PPNET_OK) return rc;
@@ -292,6 +314,21 @@ extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_p
         if ((rc = slot_reserve(s, 3, b_bt * nm + 16)) != PPNET_OK) return rc;
         if ((rc = slot_reserve(s, 4, b_small * nm + 64)) != PPNET_OK) return rc;
         if ((rc = slot_reserve(s, 5, 64)) != PPNET_OK) return rc;
+        if (io) {
+            if (io->segs_rc_f64 && (rc = slot_reserve(s, 6, 32 * (size_t)ns)) != PPNET_OK) return rc;
+            if (io->segs_xy_f32 && (rc = slot_reserve(s, 7, 16 * (size_t)ns)) != PPNET_OK) return rc;
+            for (int v = 8; v <= 10; ++v)
+                if ((rc = slot_reserve(s, v, (size_t)ns)) != PPNET_OK) return rc;
+            // the segment uploads go first: they overlap the previous slice's kernels and downloads
+            if (io->segs_rc_f64) {
+                PPNET_CUDA(cudaMemcpyAsync(s.buf[6], io->segs_rc_f64 + 4 * m0 * spm, 32 * (size_t)ns, cudaMemcpyHostToDevice, s.st));
+                c->h2d_bytes += 32 * ns;
+            }
+            if (io->segs_xy_f32) {
+                PPNET_CUDA(cudaMemcpyAsync(s.buf[7], io->segs_xy_f32 + 4 * m0 * spm, 16 * (size_t)ns, cudaMemcpyHostToDevice, s.st));
+                c->h2d_bytes += 16 * ns;
+            }
+        }
         char* small = (char*)s.buf[4];
         double* d_angle = (double*)small;
         int32_t* d_trans = (int32_t*)(small + 8 * nm);
@@ -308,11 +345,24 @@ extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_p
         q.out_pathpt = p->out_pathpt ? (double*)s.buf[0] : nullptr;
         q.out_segpt = p->out_segpt ? (double*)s.buf[1] : nullptr;
         q.out_obs = (double*)s.buf[2];
-        q.out_bits = p->out_bits ? (uint32_t*)s.buf[3] : nullptr;
+        q.out_bits = need_bits ? (uint32_t*)s.buf[3] : nullptr;
         q.out_angle = d_angle; q.out_trans = d_trans; q.out_obs_cnt = d_ocnt; q.out_rand_cnt = d_rcnt;
         q.out_tries = d_tries; q.out_valid = d_valid;
         q.counters = (unsigned long long*)s.buf[5];
         if ((rc = ppnet_generate_maps(&q, (void*)s.st)) != PPNET_OK) return rc;
+        if (io) {
+            if (io->verdict_f64 &&
+                (rc = ppnet_segcheck_edage_f64((const double*)s.buf[6], ns, nullptr, spm, nm, (const double*)s.buf[2], d_ocnt,
+                                               (int32_t)oo, io->clearance_px, io->bound, io->dot_mode, (uint8_t*)s.buf[8],
+                                               (void*)s.st)) != PPNET_OK) return rc;
+            if (io->verdict_f32 &&
+                (rc = ppnet_segcheck_mpnet_f32((const float*)s.buf[7], ns, nullptr, spm, nm, (const double*)s.buf[2], d_ocnt,
+                                               (int32_t)oo, io->clearance_px, io->bound, (uint8_t*)s.buf[9], nullptr,
+                                               (void*)s.st)) != PPNET_OK) return rc;
+            if (io->verdict_dda &&
+                (rc = ppnet_dda_gridcheck((const uint32_t*)s.buf[3], R, nm, (const float*)s.buf[7], ns, nullptr, spm,
+                                          (uint8_t*)s.buf[10], nullptr, (void*)s.st)) != PPNET_OK) return rc;
+        }
 #define PPNET_D2H(host, devp, bytes)                                                                        \
     if (host) {                                                                                             \
         PPNET_CUDA(cudaMemcpyAsync((char*)(host), devp, (bytes), cudaMemcpyDeviceToHost, s.st));            \
@@ -328,8 +378,13 @@ extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_p
         PPNET_D2H(p->out_rand_cnt ? p->out_rand_cnt + m0 : nullptr, d_rcnt, 4 * (size_t)nm);
         PPNET_D2H(p->out_tries ? p->out_tries + m0 : nullptr, d_tries, 4 * (size_t)nm);
         PPNET_D2H(p->out_valid ? p->out_valid + m0 : nullptr, d_valid, (size_t)nm);
+        if (io) {
+            PPNET_D2H(io->verdict_f64 ? io->verdict_f64 + m0 * spm : nullptr, s.buf[8], (size_t)ns);
+            PPNET_D2H(io->verdict_f32 ? io->verdict_f32 + m0 * spm : nullptr, s.buf[9], (size_t)ns);
+            PPNET_D2H(io->verdict_dda ? io->verdict_dda + m0 * spm : nullptr, s.buf[10], (size_t)ns);
+        }
         if (p->counters)
-            PPNET_CUDA(cudaMemcpyAsync(cnt_keep.data() + 4 * k, s.buf[5], 32, cudaMemcpyDeviceToHost, s.st));
+            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 4 * k, s.buf[5], 32, cudaMemcpyDeviceToHost, s.st));
     }
     PPNET_CUDA(cudaStreamSynchronize(c->slot[0].st));
     PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
@@ -337,6 +392,16 @@ extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_p
         for (int64_t q = 0; q < n_slices; ++q)
             for (int i = 0; i < 4; ++i) p->counters[i] += cnt_keep[4 * q + i];
     return PPNET_OK;
+}
+
+extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* p) {
+    return generate_host_impl((Ctx*)ctx, (Bank*)bank, p, nullptr);
+}
+
+extern "C" int ppnet_generate_and_check_host(void* ctx, void* bank, const ppnet_gen_params* p,
+                                             const ppnet_pipeline_io* io) {
+    PPNET_REQUIRE(io, "generate_and_check_host: null io");
+    return generate_host_impl((Ctx*)ctx, (Bank*)bank, p, io);
 }
 
 extern "C" int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t resolution, int64_t n_maps,

@@ -114,6 +114,14 @@ class HostContext:
         return out
 
 
+class PipelineIO(ctypes.Structure):
+    """Mirror of `ppnet_pipeline_io` (include/ppnet_b200.h)."""
+    _fields_ = [("segs_rc_f64", ctypes.c_void_p), ("segs_xy_f32", ctypes.c_void_p), ("segs_per_map", ctypes.c_int64),
+                ("clearance_px", ctypes.c_double), ("bound", ctypes.c_double), ("dot_mode", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("verdict_f64", ctypes.c_void_p), ("verdict_f32", ctypes.c_void_p),
+                ("verdict_dda", ctypes.c_void_p)]
+
+
 class HostBank:
     """Device copy of a target-path bank built from host arrays (ppnet_bank_upload)."""
 
@@ -144,10 +152,13 @@ class HostBank:
 
 
 def generate_maps_host(ctx, bank, map0, n_maps, reps, obstacles_num, out, resolution=224, map_size=50.0,
-                       obstacle_size=5.0, clearance=1.0, seed=DEFAULT_SEED, max_tries=4096, raster_inflate=0.0):
+                       obstacle_size=5.0, clearance=1.0, seed=DEFAULT_SEED, max_tries=4096, raster_inflate=0.0, checks=None):
     """MapGenerate.generate into HOST arrays.  `out` is a dict of preallocated numpy arrays with any of the keys
     angle f64[n], trans i32[n,2], segpt f64[n,S+1,2], pathpt f64[n,Np,2], obs f64[n,O+pomax,3], obs_cnt i32[n],
-    rand_cnt i32[n], bits u32[n,R,W], tries i32[n], valid u8[n], counters u64[4]."""
+    rand_cnt i32[n], bits u32[n,R,W], tries i32[n], valid u8[n], counters u64[4].
+    `checks` (optional dict) fuses the verdicts on the fresh maps into the same call (ppnet_generate_and_check_host):
+    segs_rc_f64 f64[n*spm,4] and/or segs_xy_f32 f32[n*spm,4], clearance_px, bound, dot_mode, and any of the uint8
+    outputs verdict_f64 (A11), verdict_f32 (A12), verdict_dda."""
     p = GenParams()
     p.map0, p.n_maps, p.reps, p.obstacles_num, p.max_tries = map0, n_maps, reps, obstacles_num, max_tries
     p.resolution, p.map_size, p.obstacle_size = float(resolution), float(map_size), float(obstacle_size)
@@ -157,5 +168,29 @@ def generate_maps_host(ctx, bank, map0, n_maps, reps, obstacles_num, out, resolu
         setattr(p, "out_" + name, a.ctypes.data if a is not None else None)
     cts = out.get("counters")
     p.counters = cts.ctypes.data if cts is not None else None
-    check(lib().ppnet_generate_maps_host(ctx._h, bank._h, ctypes.byref(p)), "ppnet_generate_maps_host")
+    if checks is None:
+        check(lib().ppnet_generate_maps_host(ctx._h, bank._h, ctypes.byref(p)), "ppnet_generate_maps_host")
+        return out
+    io = PipelineIO()
+    s64, s32 = checks.get("segs_rc_f64"), checks.get("segs_xy_f32")
+    if s64 is not None:
+        s64 = _c(s64, np.float64, "segs_rc_f64")
+        io.segs_rc_f64 = s64.ctypes.data
+    if s32 is not None:
+        s32 = _c(s32, np.float32, "segs_xy_f32")
+        io.segs_xy_f32 = s32.ctypes.data
+    n_seg = (len(s64) if s64 is not None else len(s32)) if (s64 is not None or s32 is not None) else 0
+    if n_maps == 0 or n_seg % max(n_maps, 1):
+        raise PPNetError("segments must be uniformly grouped: len(segs) divisible by n_maps")
+    io.segs_per_map = n_seg // n_maps
+    io.clearance_px, io.bound, io.dot_mode = float(checks["clearance_px"]), float(checks.get("bound", DEFAULT_BOUND)), \
+        int(checks.get("dot_mode", DOT_FUSED_SKX))
+    for name in ("verdict_f64", "verdict_f32", "verdict_dda"):
+        a = checks.get(name)
+        if a is not None:
+            if a.dtype != np.uint8 or a.size != n_seg:
+                raise PPNetError("%s must be uint8[%d]" % (name, n_seg))
+            setattr(io, name, a.ctypes.data)
+    check(lib().ppnet_generate_and_check_host(ctx._h, bank._h, ctypes.byref(p), ctypes.byref(io)),
+          "ppnet_generate_and_check_host")
     return out

@@ -171,3 +171,43 @@ def test_mapgenerate_mirror_end_to_end(tmp_path):
         assert one.shape == (3, 224, 224) and one.is_cuda
     finally:
         os.chdir(cwd)
+
+
+def test_fused_host_call_equals_the_device_ops():
+    """ppnet_generate_and_check_host (HOST buffers, slices on two streams) == generate_maps + the three verdict
+    kernels called one by one on device tensors, byte for byte; ragged last slice included."""
+    from ppnet_b200 import host, ops
+    from ppnet_b200.synthetic import synthetic_bank, synthetic_segments
+    M, SPM, R, O, reps, seed, map0 = 2500, 96, 224, 50, 10, 99, 12345
+    bk = synthetic_bank(20, seed=3)
+    keys = ("pathpt", "segpt", "hull", "hull_cnt", "obs", "obs_cnt")
+    dbank = ops.PathBank(*[torch.from_numpy(bk[k]).cuda() for k in keys])
+    hbank = host.HostBank(*[bk[k] for k in keys], device=0)
+    ctx = host.HostContext(0)
+    s64 = synthetic_segments(M, SPM, seed=5)
+    s32 = s64.astype(np.float32)
+    pomax, np_, ns1 = bk["obs"].shape[1], bk["pathpt"].shape[1], bk["segpt"].shape[1]
+    hout = dict(angle=np.empty(M), trans=np.empty([M, 2], np.int32), segpt=np.empty([M, ns1, 2]), pathpt=np.empty([M, np_, 2]),
+                obs=np.zeros([M, O + pomax, 3]), obs_cnt=np.empty(M, np.int32), rand_cnt=np.empty(M, np.int32),
+                bits=np.empty([M, R, 7], np.int32), tries=np.empty(M, np.int32), valid=np.empty(M, np.uint8),
+                counters=np.zeros(4, np.uint64))
+    v64, v32, vd = (np.empty(M * SPM, np.uint8) for _ in range(3))
+    host.generate_maps_host(ctx, hbank, map0, M, reps, O, hout, R, 50.0, 5.0, 1.0, seed, raster_inflate=2.24,
+                            checks=dict(segs_rc_f64=s64, segs_xy_f32=s32, clearance_px=C, verdict_f64=v64, verdict_f32=v32,
+                                        verdict_dda=vd))
+    gen = ops.generate_maps(dbank, map0, M, reps, O, R, 50.0, 5.0, 1.0, seed, raster_inflate=2.24)
+    w64 = ops.segcheck_edage_f64(torch.from_numpy(s64).cuda(), gen.obs, gen.obs_cnt, C)
+    w32 = ops.segcheck_mpnet_f32(torch.from_numpy(s32).cuda(), gen.obs, gen.obs_cnt, C)
+    wd = ops.dda_gridcheck(gen.bits, R, torch.from_numpy(s32).cuda(), want_first=False)
+    for name, dname in (("angle", "angle"), ("trans", "trans"), ("segpt", "segpt"), ("pathpt", "pathpt"), ("obs_cnt", "obs_cnt"),
+                        ("rand_cnt", "rand_cnt"), ("bits", "bits"), ("tries", "tries"), ("valid", "valid")):
+        assert np.array_equal(hout[name], getattr(gen, dname).cpu().numpy()), name
+    cnt = hout["obs_cnt"]
+    dobs = gen.obs.cpu().numpy()
+    for m in range(0, M, 97):
+        assert np.array_equal(hout["obs"][m, :cnt[m]], dobs[m, :cnt[m]])
+    assert np.array_equal(v64, w64.cpu().numpy()) and np.array_equal(v32, w32.cpu().numpy())
+    assert np.array_equal(vd, wd.cpu().numpy())
+    assert hout["counters"][0] == M and hout["counters"][1] == int(hout["valid"].sum())
+    h2d, d2h = ctx.bytes_moved()
+    assert h2d == M * SPM * 48 and d2h > M * SPM * 3
