@@ -164,7 +164,27 @@ def run_reference(args):
                                    "step (R=224, O=50, 1024 segments/map, clearance 1)" % sample_maps},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank's threads to the CPUs next to its GPU (sysfs local_cpulist) so that the pinned host buffers it
+    allocates afterwards are first-touched on the GPU's NUMA node: the e2e path is host<->device copies."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return "%s -> %d cpus" % (bdf, len(cpus))
+    except Exception as e:                                   # containers without sysfs access: leave the affinity alone
+        return "unbound (%s)" % type(e).__name__
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -182,6 +202,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     M = args.maps
@@ -299,6 +320,9 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         ctx = host.HostContext(local)
+        ctx_gmm = host.HostContext(local)                    # second context (own streams / arena) for the GMM sampler
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1)             # contexts are thread-safe when distinct; ctypes drops the GIL
         hbank = host.HostBank(bk["pathpt"], bk["segpt"], bk["hull"], bk["hull_cnt"], bk["obs"], bk["obs_cnt"], device=local)
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
         hout = dict(angle=pin([M], torch.float64), trans=pin([M, 2], torch.int32),
@@ -318,14 +342,15 @@ def run_ours(args):
             # one host call: upload this step's candidate segments, generate the maps, run the three verdict kernels
             # against them, download labels / obstacle sets / bitmaps / verdicts (copies overlap kernels slice by slice)
             map0, _ = sharding.step_range(it, rank, world, M)
+            fut = pool.submit(ctx_gmm.gmm_sample, SEED, map0 * GMM_PER_MAP, n_gmm, gm, gs, gw, out=hgmm)   # D2H-only, rides under the uploads
             host.generate_maps_host(ctx, hbank, map0, M, REPS, O, hout, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED,
                                     raster_inflate=clear_px / 2, checks=checks)
-            ctx.gmm_sample(SEED, map0 * GMM_PER_MAP, n_gmm, gm, gs, gw, out=hgmm)
+            fut.result()
 
         e2e_steps = max(2, min(args.steps, 5))
         for it in range(2):
             e2e_step(it)
-        b0 = ctx.bytes_moved()
+        b0 = [a + b for a, b in zip(ctx.bytes_moved(), ctx_gmm.bytes_moved())]
         barrier()
         t0 = time.perf_counter()
         for it in range(e2e_steps):
@@ -335,7 +360,7 @@ def run_ours(args):
                 print("e2e step %d: %.2f ms" % (it, 1e3 * (time.perf_counter() - ta)), file=sys.stderr)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        b1 = ctx.bytes_moved()
+        b1 = [a + b for a, b in zip(ctx.bytes_moved(), ctx_gmm.bytes_moved())]
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -345,7 +370,8 @@ def run_ours(args):
                "h2d_bytes_per_step": (b1[0] - b0[0]) // e2e_steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // e2e_steps,
                "ms_per_step": 1e3 * dt / e2e_steps, "valid_paths_per_s": M * world * e2e_steps / dt,
                "timer": "host wall clock around synchronous host-API calls (each call synchronises before returning)",
-               "api": "ppnet_generate_and_check_host + ppnet_gmm_sample_host, pinned host buffers"}
+               "api": "ppnet_generate_and_check_host + ppnet_gmm_sample_host (second context, concurrent), pinned host buffers",
+               "cpu_affinity": numa}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -367,12 +393,30 @@ def run_ours(args):
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "counts_all_gathered": {"maps": maps_done, "valid_paths": valid,
                                                           "accepted_obstacles": acc_obs, "placement_tries": tries}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries (NCCL prints its version banner) write to fd 1
+    behind Python's back: point fd 1 at stderr for the whole run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
