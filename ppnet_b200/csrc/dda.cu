@@ -242,7 +242,7 @@ extern "C" int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int
     const size_t smem = ((bm_bytes + 15) & ~(size_t)15) + 16 + (size_t)kDdaStage * (16 + 2 + 2);
     PPNET_REQUIRE(smem <= 220 * 1024, "dda: resolution too large for a shared-memory bitmap");
     // big bitmaps: amortise the staging over every segment of the map; small ones: more CTAs in flight
-    const int chunk = bm_bytes >= 64 * 1024 ? 8192 : 1024;
+    const int chunk = bm_bytes >= 64 * 1024 ? 8192 : kDdaStage;
     const int64_t chunks = (segs_per_map + chunk - 1) / chunk;
     PPNET_REQUIRE(chunks <= 65535, "dda: too many segments in one map");
     if (smem > 48 * 1024)

@@ -11,13 +11,15 @@
 //      `while` of the reference).  In parity mode the draws come from the caller instead.
 //   2. all threads rotate/translate the 1000 path points + 11 segment points (label, 16.2 KB -- the
 //      dominant HBM stream, written with 16-byte stores) and keep the odd-indexed points in shared memory.
-//   3. candidate circles: thread k draws candidate k once; each warp then owns candidates round-robin.  The
-//      staged odd points are grouped into boxes of 16 consecutive points; a lane owns a box, skips it when the
+//   3. candidate circles: thread k draws candidate k once.  The staged odd points are grouped into boxes of 16
+//      consecutive points; the (candidate, box) pairs are spread flat over the CTA: a pair is skipped when the
 //      candidate is farther from the box than the threshold plus a 1e7-ulp margin (those points cannot be the
-//      ones that decide `min(dis) > r_px + c*R/M`), otherwise evaluates its points with the reference's exact
-//      un-fused arithmetic.  One sqrt per candidate; ordered compaction by ballot scan.
+//      ones that decide `min(dis) > r_px + c*R/M`), otherwise its points are evaluated with the reference's exact
+//      un-fused arithmetic and folded into the candidate's minimum by a shared-memory atomicMin on the bit
+//      pattern.  One sqrt per candidate; ordered compaction by ballot scan.
 //   4. the path-hugging obstacles of the target path are placed with the same rigid transform and appended.
-//   5. optional: all obstacles rasterised into a shared-memory bitmap and streamed out.
+//   5. optional: all obstacles rasterised into a shared-memory bitmap -- (disk, row) span tasks spread flat over
+//      the CTA through a prefix over the disks' row counts -- and streamed out.
 // The target-path bank (16 KB / path) is read through L2; nothing else is read from HBM.
 #include <math_constants.h>
 
@@ -109,7 +111,7 @@ generate_kernel(ppnet_gen_params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: odd points [np/2] double2 | hull [hmax] double2 | bitmap [R*W padded to 4] words (optional) |
     //         obstacle triples [O + pomax] x 3 doubles (candidate k at slot k, path obstacle k at slot O + k) |
-    //         accept flags [O]
+    //         per-candidate threshold / cull radius / running min d^2 [O] each | raster task prefix | accept flags [O]
     const int n_odd = P.np / 2;
     const int O = P.obstacles_num;
     const int omax_out = O + P.pomax;
@@ -121,7 +123,12 @@ generate_kernel(ppnet_gen_params P) {
     double4* box = reinterpret_cast<double4*>(hull + P.hmax + (P.hmax & 1));    // (row_lo, row_hi, col_lo, col_hi), 32-B aligned
     uint32_t* bm = reinterpret_cast<uint32_t*>(box + n_blk);
     double* sobs = reinterpret_cast<double*>(bm + ((words + 3) & ~3));
-    uint8_t* acc_s = reinterpret_cast<uint8_t*>(sobs + 3 * omax_out);
+    double* thr_s = sobs + 3 * omax_out;                                       // [O] r_px + c_px
+    double* cull_s = thr_s + O;                                                // [O] squared cull radius
+    unsigned long long* m2_s = reinterpret_cast<unsigned long long*>(cull_s + O);   // [O] bits of min d^2 (non-negative doubles order like integers)
+    int* task_s = reinterpret_cast<int*>(m2_s + O);                            // [omax_out + 1] prefix of raster row tasks
+    int* row0_s = task_s + omax_out + 1;                                       // [omax_out] first row of each disk
+    uint8_t* acc_s = reinterpret_cast<uint8_t*>(row0_s + omax_out);
     __shared__ GenShared sh;
 
     const int64_t lm = blockIdx.x;                        // local map index
@@ -243,34 +250,39 @@ generate_kernel(ppnet_gen_params P) {
             draw_candidate(key, g, k, O, M, P.obstacle_size, x, y, r);
         }
         double* o = sobs + 3 * k;                          // [coord_img[1], coord_img[0], radius_img]  (:134-136, :143)
-        o[0] = __dmul_rn(__ddiv_rn(y, M), R);
-        o[1] = __dmul_rn(__ddiv_rn(x, M), R);
-        o[2] = __dmul_rn(__ddiv_rn(r, M), R);
-    }
-    __syncthreads();
-    for (int k = warp; k < O; k += kGenWarps) {
-        const double q1 = sobs[3 * k], q0 = sobs[3 * k + 1], rimg = sobs[3 * k + 2];
+        const double q1 = __dmul_rn(__ddiv_rn(y, M), R), q0 = __dmul_rn(__ddiv_rn(x, M), R);
+        const double rimg = __dmul_rn(__ddiv_rn(r, M), R);
+        o[0] = q1; o[1] = q0; o[2] = rimg;
         const double thr = __dadd_rn(rimg, thr_c);
         // squared cull radius: (thr + margin)^2 with the margin ~1e7 ulp of the coordinates involved
         const double cr = thr + 1e-9 * (R + fabs(q0) + fabs(q1) + fabs(thr));
-        const double cull2 = cr * cr * (1.0 + 1e-12);
+        thr_s[k] = thr;
+        cull_s[k] = cr * cr * (1.0 + 1e-12);
+        m2_s[k] = 0x7ff0000000000000ull;                   // +inf
+    }
+    __syncthreads();
+    // flat (candidate, box) pairs over the whole CTA: a pair whose box is farther than the cull radius cannot hold
+    // the point that decides `min(dis) > r_px + c_px`; the others evaluate their 16 points with the reference's
+    // un-fused arithmetic and fold into the candidate's minimum with one shared-memory atomicMin.
+    for (int t = threadIdx.x; t < O * n_blk; t += kGenThreads) {
+        const int k = t / n_blk, b = t - k * n_blk;
+        const double q1 = sobs[3 * k], q0 = sobs[3 * k + 1];
+        const double4 bb = box[b];
+        const double ex = fmax(fmax(bb.x - q0, q0 - bb.y), 0.0), ey = fmax(fmax(bb.z - q1, q1 - bb.w), 0.0);
+        if (ex * ex + ey * ey > cull_s[k]) continue;       // NaN never culls
         double m2 = CUDART_INF;
-        for (int b = lane; b < n_blk; b += 32) {
-            const double4 bb = box[b];
-            const double ex = fmax(fmax(bb.x - q0, q0 - bb.y), 0.0), ey = fmax(fmax(bb.z - q1, q1 - bb.w), 0.0);
-            if (ex * ex + ey * ey > cull2) continue;       // NaN never culls
-            const int e = min(n_odd, (b + 1) * kBlkPts);
-            for (int i = b * kBlkPts; i < e; ++i) {
-                const double2 p = odd[i];
-                const double ax = __dsub_rn(p.x, q0), ay = __dsub_rn(p.y, q1);     // scipy euclidean: un-fused
-                m2 = fmin(m2, __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
-            }
+        const int e = min(n_odd, (b + 1) * kBlkPts);
+        for (int i = b * kBlkPts; i < e; ++i) {
+            const double2 p = odd[i];
+            const double ax = __dsub_rn(p.x, q0), ay = __dsub_rn(p.y, q1);         // scipy euclidean: un-fused
+            m2 = fmin(m2, __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
         }
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, sft));
+        atomicMin(m2_s + k, (unsigned long long)__double_as_longlong(m2));
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < O; k += kGenThreads) {
         // sqrt is monotone: sqrt(min d^2) == min sqrt(d^2); skipped boxes only hold points with d > thr
-        const bool ok = __dsqrt_rn(m2) > thr;                                     // :142
-        if (lane == 0) acc_s[k] = ok ? 1 : 0;
+        acc_s[k] = __dsqrt_rn(__longlong_as_double((long long)m2_s[k])) > thr_s[k] ? 1 : 0;   // :142
     }
     __syncthreads();
     // ordered compaction of the accepted candidates (the reference appends in loop order)
@@ -321,9 +333,39 @@ generate_kernel(ppnet_gen_params P) {
     // ---- 5. occupancy bitmap ----------------------------------------------------------------------------
     if (P.out_bits) {
         __syncthreads();
-        for (int k = warp; k < O + n_po; k += kGenWarps) {
-            if (k < O && !acc_s[k]) continue;              // rejected candidate
-            raster_disk_warp(bm, (int)R, W, sobs[3 * k], sobs[3 * k + 1], __dadd_rn(sobs[3 * k + 2], P.raster_inflate));
+        // (disk, row) tasks flattened over the CTA: every thread gets the same number of row spans whatever the radii
+        const int n_disk = O + n_po;
+        for (int k = threadIdx.x; k < n_disk; k += kGenThreads) {
+            int i0 = 0, i1 = 0;
+            if (k >= O || acc_s[k])                        // rejected candidates paint nothing
+                disk_rows((int)R, sobs[3 * k], sobs[3 * k + 1], __dadd_rn(sobs[3 * k + 2], P.raster_inflate), i0, i1);
+            row0_s[k] = i0;
+            task_s[k] = i1 - i0;
+        }
+        __syncthreads();
+        if (warp == 0) {                                   // exclusive prefix of the row counts
+            int carry = 0;
+            for (int k0 = 0; k0 < n_disk; k0 += 32) {
+                const int k = k0 + lane;
+                const int v = k < n_disk ? task_s[k] : 0;
+                int inc = v;
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, inc, sft);
+                    if (lane >= sft) inc += o;
+                }
+                if (k < n_disk) task_s[k] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) task_s[n_disk] = carry;
+        }
+        __syncthreads();
+        const int total = task_s[n_disk];
+        int k = 0;                                         // tasks of one thread ascend: walk the prefix forward
+        for (int t = threadIdx.x; t < total; t += kGenThreads) {
+            while (t >= task_s[k + 1]) ++k;
+            raster_disk_row(bm, (int)R, W, sobs[3 * k], sobs[3 * k + 1], __dadd_rn(sobs[3 * k + 2], P.raster_inflate),
+                            row0_s[k] + (t - task_s[k]));
         }
         __syncthreads();
         store_bitmap(bm, P.out_bits + (size_t)lm * words, words);
@@ -374,7 +416,8 @@ extern "C" int ppnet_generate_maps(const ppnet_gen_params* p, void* stream) {
     PPNET_REQUIRE((p->in_angle == nullptr) == (p->in_trans == nullptr), "generate_maps: in_angle and in_trans go together");
     const int R = (int)p->resolution, W = (R + 31) / 32;
     size_t smem = sizeof(double2) * (size_t)(p->np / 2 + p->hmax + 1) + 32 * (size_t)((p->np / 2 + kBlkPts - 1) / kBlkPts) +
-                  sizeof(double) * 3 * (size_t)(p->obstacles_num + p->pomax) + (size_t)p->obstacles_num + 64;
+                  sizeof(double) * 3 * (size_t)(p->obstacles_num + p->pomax) + 24 * (size_t)p->obstacles_num +
+                  8 * (size_t)(p->obstacles_num + p->pomax + 2) + (size_t)p->obstacles_num + 64;
     if (p->out_bits) smem += (size_t)(((R * W) + 3) & ~3) * 4;
     PPNET_REQUIRE(smem <= 220 * 1024, "generate_maps: shared memory budget exceeded (%zu bytes)", smem);
     if (smem > 48 * 1024)

@@ -21,6 +21,36 @@ __device__ __forceinline__ void or_span(uint32_t* row, int j0, int j1) {   // in
     }
 }
 
+// Row range [i0, i1) a disk can touch (empty for degenerate disks)
+__device__ __forceinline__ void disk_rows(int R, double ox, double oy, double rr, int& i0, int& i1) {
+    i0 = i1 = 0;
+    if (!(rr > 0.0) || !(ox == ox) || !(oy == oy) || isinf(rr) || isinf(ox) || isinf(oy)) return;
+    const double lo_f = floor(oy - rr - 1.0), hi_f = ceil(oy + rr + 1.0);
+    i0 = lo_f < 0.0 ? 0 : (lo_f > (double)R ? R : (int)lo_f);
+    i1 = hi_f > (double)R ? R : (hi_f < 0.0 ? 0 : (int)hi_f);
+}
+
+// One (disk, row) task: the inside set of a row is an interval (every rounded op is monotone in |dx|): guess its
+// ends from sqrt, then settle them with the exact per-pixel rule.
+__device__ __forceinline__ void raster_disk_row(uint32_t* bm, int R, int W, double ox, double oy, double rr, int i) {
+    const double r2 = __dmul_rn(rr, rr);
+    const double dy = __dsub_rn(__dadd_rn((double)i, 0.5), oy);
+    const double dy2 = __dmul_rn(dy, dy);
+    if (!(dy2 <= r2)) return;                              // even dx = 0 fails
+    const double hw = sqrt(r2 - dy2);
+    double a = ceil(ox - hw - 0.5), b = floor(ox + hw - 0.5);
+    a = fmin(fmax(a, -2.0), (double)R + 1.0);
+    b = fmin(fmax(b, -2.0), (double)R + 1.0);
+    int j0 = (int)a, j1 = (int)b;
+    while (j0 > -2 && px_inside(ox, dy2, r2, j0 - 1)) --j0;
+    while (j0 <= j1 && !px_inside(ox, dy2, r2, j0)) ++j0;
+    while (j1 < R + 1 && px_inside(ox, dy2, r2, j1 + 1)) ++j1;
+    while (j1 >= j0 && !px_inside(ox, dy2, r2, j1)) --j1;
+    j0 = max(j0, 0);
+    j1 = min(j1, R - 1);
+    if (j0 <= j1) or_span(bm + i * W, j0, j1);
+}
+
 // One warp rasterises one disk into bm[R][W] (shared memory): one row span per lane.
 __device__ __forceinline__ void raster_disk_warp(uint32_t* bm, int R, int W, double ox, double oy, double rr) {
     const int lane = threadIdx.x & 31;
