@@ -268,7 +268,7 @@ struct __align__(16) SegSlot {                   // what a pair needs of its seg
 };
 
 template <typename T, int MODE, bool SWAP, bool STEER>
-__global__ void __launch_bounds__(kSegThreads, 3)
+__global__ void __launch_bounds__(kSegThreads, 4)
 segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
                 const double* __restrict__ obs, const int32_t* __restrict__ obs_cnt, int omax,
                 double clearance, T bound, uint8_t* __restrict__ verdict, uint8_t* __restrict__ steer) {
@@ -428,7 +428,7 @@ segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, 
             __syncwarp();
             if (have) {
                 hit = hit || ((hitmask[warp] >> lane) & 1u);
-                if (verdict && (last_tile || hit)) verdict[cur] = hit ? 1 : 0;
+                if (verdict && (first_tile || hit)) verdict[cur] = hit ? 1 : 0;     // later tiles read it back
                 if (STEER && steer && last_tile) {
                     // steerTo: dist = euclidean(start, end) in f32 (un-fused); 0 iff dist > 0 and blocked.
                     // sqrt(x) > 0  <=>  x > 0  (and NaN stays false), so the root itself is not needed.
