@@ -12,7 +12,8 @@
 //   2. all threads rotate/translate the 1000 path points + 11 segment points (label, 16.2 KB -- the
 //      dominant HBM stream, written with 16-byte stores) and keep the odd-indexed points in shared memory.
 //   3. candidate circles: thread k draws candidate k once.  The staged odd points are grouped into boxes of 16
-//      consecutive points; the (candidate, box) pairs are spread flat over the CTA: a pair is skipped when the
+//      consecutive points; the (candidate, box) pairs are spread over the CTA (warp = candidate, lane = box,
+//      no cross-lane reduction): a pair is skipped when the
 //      candidate is farther from the box than the threshold plus a 1e7-ulp margin (those points cannot be the
 //      ones that decide `min(dis) > r_px + c*R/M`), otherwise its points are evaluated with the reference's exact
 //      un-fused arithmetic and folded into the candidate's minimum by a shared-memory atomicMin on the bit
@@ -264,20 +265,21 @@ generate_kernel(ppnet_gen_params P) {
     // flat (candidate, box) pairs over the whole CTA: a pair whose box is farther than the cull radius cannot hold
     // the point that decides `min(dis) > r_px + c_px`; the others evaluate their 16 points with the reference's
     // un-fused arithmetic and fold into the candidate's minimum with one shared-memory atomicMin.
-    for (int t = threadIdx.x; t < O * n_blk; t += kGenThreads) {
-        const int k = t / n_blk, b = t - k * n_blk;
-        const double q1 = sobs[3 * k], q0 = sobs[3 * k + 1];
-        const double4 bb = box[b];
-        const double ex = fmax(fmax(bb.x - q0, q0 - bb.y), 0.0), ey = fmax(fmax(bb.z - q1, q1 - bb.w), 0.0);
-        if (ex * ex + ey * ey > cull_s[k]) continue;       // NaN never culls
-        double m2 = CUDART_INF;
-        const int e = min(n_odd, (b + 1) * kBlkPts);
-        for (int i = b * kBlkPts; i < e; ++i) {
-            const double2 p = odd[i];
-            const double ax = __dsub_rn(p.x, q0), ay = __dsub_rn(p.y, q1);         // scipy euclidean: un-fused
-            m2 = fmin(m2, __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+    for (int k = warp; k < O; k += kGenWarps) {            // warp <-> candidate, lane <-> box: no index arithmetic
+        const double q1 = sobs[3 * k], q0 = sobs[3 * k + 1], cull2 = cull_s[k];
+        for (int b = lane; b < n_blk; b += 32) {
+            const double4 bb = box[b];
+            const double ex = fmax(fmax(bb.x - q0, q0 - bb.y), 0.0), ey = fmax(fmax(bb.z - q1, q1 - bb.w), 0.0);
+            if (ex * ex + ey * ey > cull2) continue;       // NaN never culls
+            double m2 = CUDART_INF;
+            const int e = min(n_odd, (b + 1) * kBlkPts);
+            for (int i = b * kBlkPts; i < e; ++i) {
+                const double2 p = odd[i];
+                const double ax = __dsub_rn(p.x, q0), ay = __dsub_rn(p.y, q1);     // scipy euclidean: un-fused
+                m2 = fmin(m2, __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+            }
+            atomicMin(m2_s + k, (unsigned long long)__double_as_longlong(m2));
         }
-        atomicMin(m2_s + k, (unsigned long long)__double_as_longlong(m2));
     }
     __syncthreads();
     for (int k = threadIdx.x; k < O; k += kGenThreads) {
@@ -361,11 +363,17 @@ generate_kernel(ppnet_gen_params P) {
         }
         __syncthreads();
         const int total = task_s[n_disk];
-        int k = 0;                                         // tasks of one thread ascend: walk the prefix forward
-        for (int t = threadIdx.x; t < total; t += kGenThreads) {
-            while (t >= task_s[k + 1]) ++k;
-            raster_disk_row(bm, (int)R, W, sobs[3 * k], sobs[3 * k + 1], __dadd_rn(sobs[3 * k + 2], P.raster_inflate),
-                            row0_s[k] + (t - task_s[k]));
+        // a contiguous run of tasks per thread: the disk index is found once (binary search), then advances rarely
+        const int per = (total + kGenThreads - 1) / kGenThreads;
+        const int t_lo = min(total, (int)threadIdx.x * per), t_hi = min(total, t_lo + per);
+        if (t_lo < t_hi) {
+            int k = 0, hi = n_disk;                        // largest k with task_s[k] <= t_lo
+            while (hi - k > 1) { const int mid = (k + hi) >> 1; if (task_s[mid] <= t_lo) k = mid; else hi = mid; }
+            for (int t = t_lo; t < t_hi; ++t) {
+                while (t >= task_s[k + 1]) ++k;
+                raster_disk_row(bm, (int)R, W, sobs[3 * k], sobs[3 * k + 1], __dadd_rn(sobs[3 * k + 2], P.raster_inflate),
+                                row0_s[k] + (t - task_s[k]));
+            }
         }
         __syncthreads();
         store_bitmap(bm, P.out_bits + (size_t)lm * words, words);
