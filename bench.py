@@ -311,10 +311,11 @@ def run_ours(args):
     tp = os.path.join(REPO, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(dom)
+            traffic = (json.load(f).get(dom) or {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "note": "analytic f64 verdict kernels are FP64-issue bound, not HBM bound (DESIGN.md)"}
+                "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full",
+                "note": "every kernel of this path is instruction-issue bound, not HBM bound (DESIGN.md 4.2)"}
 
     # ---- e2e through the host-buffer C ABI: pinned host inputs -> host outputs, copies inside the timed region
     e2e = None
