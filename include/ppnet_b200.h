@@ -267,6 +267,19 @@ typedef struct ppnet_path_params {
 } ppnet_path_params;
 int ppnet_path_synthesize(const ppnet_path_params* params, void* stream);
 
+/* ---- "next" rows ------------------------------------------------------------------------------
+ * N2  process_map.generate_gen_path  EDaGe-PP/process_map.py:148-163: out[M][R][R] uint8, 255 at round(p) of every
+ *     `stride`-th (5th) label point with 0 < row, col < R, 0 elsewhere (the PNG encoding stays with the caller).   */
+int ppnet_path_mask(const double* pathpt, int32_t np, int64_t n_maps, int32_t stride, int32_t resolution, uint8_t* out,
+                    void* stream);
+/* N3  process_map.extract_path  EDaGe-PP/process_map.py:293-365: greedy 8-neighbour walk on the down-sampled heat-map
+ *     mask[n][h][w] float32 from init_state/ds towards end_state/ds.  out[n][max_len + 2][2] = init_state,
+ *     ds * walk..., end_state; out_len[n] = number of rows (0 on failure); ok[n].  The reference's 1 s wall-clock
+ *     timeout becomes the step budget max_len.                                                                    */
+int ppnet_extract_path(const float* mask, int32_t h, int32_t w, const double* init_state, const double* end_state,
+                       double down_sample_rate, int64_t n, int32_t max_len, double* out, int32_t* out_len, uint8_t* ok,
+                       void* stream);
+
 /* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
 int ppnet_ctx_create(int32_t device, void** ctx);
 int ppnet_ctx_destroy(void* ctx);

@@ -723,6 +723,85 @@ def add_init_end_single(image, init, end):
 
 
 # --------------------------------------------------------------------------------------------
+# N1 / A7 (mask): torchvision's RandomRotation(degrees=(d, d)) + functional.affine(translate) + crop on a mask
+#   (Path.py:160-161, 175-178; MapGenerate.py:102-106; process_map.py:174-178)
+# --------------------------------------------------------------------------------------------
+def mask_rigid(src, angle_deg, translate, out_size):
+    """src u8[Ws,Ws]; two nearest-neighbour passes: out(i, j) = rot(rint(i - ty), rint(j - tx)), rot(i2, j2) =
+    src(rint(sin*x + cos*y + c), rint(cos*x - sin*y + c)), x = j2 - c, y = i2 - c, c = (Ws-1)/2, angle d."""
+    src = np.asarray(src)
+    ws = src.shape[0]
+    ii, jj = np.meshgrid(np.arange(out_size), np.arange(out_size), indexing="ij")
+    j2 = np.rint(jj - f64(translate[0]))
+    i2 = np.rint(ii - f64(translate[1]))
+    c = 0.5 * (ws - 1)
+    th = f64(angle_deg) / 180.0 * np.pi
+    x, y = j2 - c, i2 - c
+    js = np.rint(np.cos(th) * x - np.sin(th) * y + c)
+    is_ = np.rint(np.sin(th) * x + np.cos(th) * y + c)
+    ok = (j2 >= 0) & (j2 < ws) & (i2 >= 0) & (i2 < ws) & (js >= 0) & (js < ws) & (is_ >= 0) & (is_ < ws)
+    out = np.zeros([out_size, out_size], dtype=src.dtype)
+    out[ok] = src[is_[ok].astype(int), js[ok].astype(int)]
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# N2  process_map.generate_gen_path (EDaGe-PP/process_map.py:148-163): every 5th label point -> 255
+# --------------------------------------------------------------------------------------------
+def gen_path_mask(path_point, resolution=224):
+    m = np.zeros([resolution, resolution], dtype=np.uint8)
+    for step, q in enumerate(np.asarray(path_point, dtype=np.float64)):
+        r0, c0 = int(np.round(q[0])), int(np.round(q[1]))
+        if step % 5 == 0 and 0 < r0 < resolution and 0 < c0 < resolution:      # strict: row / col 0 are never painted
+            m[r0, c0] = 255
+    return m
+
+
+# --------------------------------------------------------------------------------------------
+# N3  process_map.extract_path (EDaGe-PP/process_map.py:293-365): greedy 8-neighbour walk on the down-sampled
+#     heat-map (the PIL bilinear down-sampling itself is third-party and stays with the caller)
+# --------------------------------------------------------------------------------------------
+_MOTIONS = [[0, 1], [0, -1], [1, 0], [-1, 0], [1, 1], [1, -1], [-1, 1], [-1, -1]]
+
+
+def extract_path_walk(mask_small, init_state, end_state, down_sample_rate, max_steps=100000):
+    """mask_small f32[h,w]; returns (ok, path f64[L,2]) with path = [init_state, ds * walk..., end_state]."""
+    mask = np.asarray(mask_small, dtype=np.float32)
+    h, w = mask.shape
+    ds = f64(down_sample_rate)
+    init = np.asarray(init_state, dtype=np.float64) / ds
+    end = np.asarray(end_state, dtype=np.float64) / ds
+    path = []
+    nxt = init
+    for _ in range(max_steps):
+        cand = [np.asarray(m, dtype=np.float64) + nxt for m in _MOTIONS]
+        val = []
+        for cpt in cand:
+            r0, c0 = int(np.round(cpt[0])), int(np.round(cpt[1]))
+            val.append(mask[r0, c0] if (0 <= r0 < h and 0 <= c0 < w) else np.float32(0))
+        while max(val) > 0:
+            ci = val.index(max(val))
+            nxt = cand[ci]
+            fresh = True
+            for i, q in enumerate(path):
+                d = np.sqrt((nxt[0] - q[0]) * (nxt[0] - q[0]) + (nxt[1] - q[1]) * (nxt[1] - q[1]))
+                if (nxt[0] == q[0] and nxt[1] == q[1]) or (d <= 1.5 and i < len(path) - 2):
+                    val[ci] = np.float32(0)
+                    fresh = False
+                    break
+            if fresh:
+                break
+        if max(val) == 0:
+            return False, np.zeros([0, 2])
+        path.append(nxt)
+        de = np.sqrt((nxt[0] - end[0]) * (nxt[0] - end[0]) + (nxt[1] - end[1]) * (nxt[1] - end[1]))
+        if de <= 2.5:
+            pts = [np.asarray(init_state, dtype=np.float64)] + [q * ds for q in path] + [np.asarray(end_state, dtype=np.float64)]
+            return True, np.asarray(pts)
+    return False, np.zeros([0, 2])
+
+
+# --------------------------------------------------------------------------------------------
 # A15  plot_obstacles -- GEOMETRIC restatement (parity UNPINNED: matplotlib/Agg/JPEG/PIL dither
 #      are not installed; see DESIGN.md).  Pixel (row i, col j) is obstacle iff its centre
 #      (j + 0.5, i + 0.5) lies inside a disk (x, y, r [+ inflate]).

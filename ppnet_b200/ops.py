@@ -493,3 +493,29 @@ def mask_rigid(src, angle_deg, translate, out_size):
     check(lib().ppnet_mask_rigid(_ptr(src), ctypes.c_int32(ws), _ptr(angle_deg), _ptr(translate), ctypes.c_int64(n),
                                  ctypes.c_int32(out_size), _ptr(out), _stream()), "ppnet_mask_rigid")
     return out
+
+
+def path_mask(pathpt, resolution=224, stride=5):
+    """N2 generate_gen_path batched (EDaGe-PP/process_map.py:148-163): pathpt f64[M,Np,2] -> u8[M,R,R]."""
+    _need(pathpt, torch.float64, "pathpt")
+    m, np_, _ = pathpt.shape
+    out = torch.empty([m, resolution, resolution], dtype=torch.uint8, device=pathpt.device)
+    check(lib().ppnet_path_mask(_ptr(pathpt), ctypes.c_int32(np_), ctypes.c_int64(m), ctypes.c_int32(stride),
+                                ctypes.c_int32(resolution), _ptr(out), _stream()), "ppnet_path_mask")
+    return out
+
+
+def extract_path(mask, init_state, end_state, down_sample_rate, max_len=4096):
+    """N3 extract_path batched (EDaGe-PP/process_map.py:293-365): mask f32[n,h,w] (already down-sampled), init/end
+    f64[n,2] -> (path f64[n,max_len+2,2], length i32[n], ok u8[n])."""
+    _need(mask, torch.float32, "mask")
+    _need(init_state, torch.float64, "init_state")
+    _need(end_state, torch.float64, "end_state")
+    n, h, w = mask.shape
+    out = torch.zeros([n, max_len + 2, 2], dtype=torch.float64, device=mask.device)
+    ln = torch.empty([n], dtype=torch.int32, device=mask.device)
+    ok = torch.empty([n], dtype=torch.uint8, device=mask.device)
+    check(lib().ppnet_extract_path(_ptr(mask), ctypes.c_int32(h), ctypes.c_int32(w), _ptr(init_state), _ptr(end_state),
+                                   ctypes.c_double(down_sample_rate), ctypes.c_int64(n), ctypes.c_int32(max_len), _ptr(out),
+                                   _ptr(ln), _ptr(ok), _stream()), "ppnet_extract_path")
+    return out, ln, ok

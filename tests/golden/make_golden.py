@@ -549,6 +549,95 @@ def gen_misc():
     print("misc.npz")
 
 
+# ---------------------------------------------------------------------------------------------
+def gen_masks():
+    """N1-N3 ("next" rows): corridor placement (MapGenerate.py:102-106), the label-mask rasterisers
+    process_map.generate_gen_path / generate_seg_space (:148-191) and extract_path (:293-365), all through the real
+    reference functions."""
+    from PIL import Image
+    mods = load_edage()
+    MG, pm = mods["MapGenerate"], mods["process_map"]
+    out = {}
+    P, O, c, seed = 2, 20, 1, 21
+    tmp = tempfile.mkdtemp(prefix="ppnet_golden_")
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    with quiet():
+        mg = MG.MapGenerate(path_num=P, resolution=224, map_size=50, obstacles_num=O, clearance=c)
+    MG.cnt = 0
+    placed = []
+    orig_affine = MG.T.functional.affine
+
+    def spy_affine(img, *a, **k):
+        r = orig_affine(img, *a, **k)
+        placed.append((r[0].cpu().numpy() * 255).round().astype(np.uint8))
+        return r
+
+    MG.T.functional.affine = spy_affine
+    try:
+        with quiet():
+            mg.generate(map_num=P * P, folder_path=os.path.join(tmp, "out"), round_index=0)
+    finally:
+        MG.T.functional.affine = orig_affine
+    n = len(mg.MapLabel)
+    assert len(placed) == n
+    spaces = [(tp.Space[0].cpu().numpy() * 255).round().astype(np.uint8) for tp in mg.PathGroup.TargetPaths]
+    out["n1_space"] = np.asarray(spaces)                                   # [P,224,224] Path.Space per target path
+    out["n1_path"] = np.asarray([(g // P) % P for g in range(n)], dtype=np.int32)
+    out["n1_angle"] = np.asarray([float(np.reshape(l[1], -1)[0]) for l in mg.MapLabel])
+    out["n1_translation"] = np.asarray([[int(l[2][0]), int(l[2][1])] for l in mg.MapLabel], dtype=np.int64)
+    out["n1_placed"] = np.asarray(placed)                                  # [n,224,224] path_space after rotate + affine
+    pathpoints = [np.asarray(l[4]) for l in mg.MapLabel]
+    segpoints = [np.asarray(l[3]) for l in mg.MapLabel]
+    out["n2_pathpoint"] = np.asarray(pathpoints)
+    out["n2_segpoint"] = np.asarray(segpoints)
+    # N2: generate_gen_path writes {root}/{index}.png ('L'); generate_seg_space writes palette PNGs of the placed corridor
+    root_p, root_s = os.path.join(tmp, "mask_path"), os.path.join(tmp, "mask_space")
+    pm.generate_gen_path(pathpoints, 0, root=root_p)
+    out["n2_gen_path"] = np.asarray([np.asarray(Image.open(os.path.join(root_p, "%d.png" % i))) for i in range(n)])
+    pm.imgviz.label_colormap = lambda: (np.arange(768) % 251).astype(np.uint8).reshape(256, 3)
+    pil_spaces = [Image.fromarray(np.stack([sp] * 3, axis=2)) for sp in spaces]
+    rot = [float(a) for a in out["n1_angle"]]
+    tr = [[int(t[0]), int(t[1])] for t in out["n1_translation"]]
+    with quiet():
+        pm.generate_seg_space(pil_spaces, pathpoints, rot, tr, 0, root=root_s)
+    out["n2_seg_space"] = np.asarray([np.asarray(Image.open(os.path.join(root_s, "%d.png" % i))) for i in range(n)])
+    # N3: extract_path on heat-maps made from the label path (3x3 dilation, values fading with distance)
+    pm.time.time = lambda: 0.0                                              # neutralise the 1 s wall-clock timeout
+    pm.time_synchronized = lambda: 0.0
+    ds = 2
+    k = 0
+    for i in range(n):
+        for variant in range(2):
+            heat = np.zeros([224, 224], dtype=np.float64)
+            for q in pathpoints[i]:
+                r0, c0 = int(np.round(q[0])), int(np.round(q[1]))
+                for dj in range(-2, 3):
+                    for dk in range(-2, 3):
+                        if 0 <= r0 + dj < 224 and 0 <= c0 + dk < 224:
+                            v = 255 - 40 * max(abs(dj), abs(dk)) - (0 if variant == 0 else (r0 * 7 + c0 * 3) % 23)
+                            heat[r0 + dj, c0 + dk] = max(heat[r0 + dj, c0 + dk], v)
+            if variant == 1:
+                heat[100:110, :] = 0                                       # a gap: the walk must fail or detour
+            img = Image.fromarray(heat.astype(np.uint8), mode="L")
+            small = img.resize((int(img.size[0] / ds), int(img.size[1] / ds)), Image.BILINEAR)
+            small = MG.T.ToTensor()(small).squeeze().numpy()
+            with quiet():
+                ok, path = pm.extract_path(img, init_state=segpoints[i][0], end_state=segpoints[i][10], down_sample_rate=ds)
+            out["n3_%d_mask" % k] = small.astype(np.float32)
+            out["n3_%d_init" % k] = np.asarray(segpoints[i][0], dtype=np.float64)
+            out["n3_%d_end" % k] = np.asarray(segpoints[i][10], dtype=np.float64)
+            out["n3_%d_ok" % k] = bool(ok)
+            out["n3_%d_path" % k] = path.numpy().astype(np.float64) if ok else np.zeros([0, 2])
+            k += 1
+    out["n3_count"], out["n3_ds"] = k, ds
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "masks.npz"), **out)
+    print("masks.npz", n, "maps", k, "extract_path cases, ok:", [bool(out["n3_%d_ok" % j]) for j in range(k)])
+
+
 GENS = {
     "segcheck_f64": lambda: gen_segcheck("f64", "segcheck_f64.npz"),
     "segcheck_f32": lambda: gen_segcheck("f32", "segcheck_f32.npz"),
@@ -556,6 +645,7 @@ GENS = {
     "paths": gen_paths,
     "mapgen": gen_mapgen,
     "misc": gen_misc,
+    "masks": gen_masks,
 }
 
 if __name__ == "__main__":

@@ -66,3 +66,38 @@ def test_parameter_struct_layouts_match_the_library():
     L.ppnet_sizeof_params.restype = ctypes.c_int64
     assert L.ppnet_sizeof_params(ctypes.c_int32(0)) == ctypes.sizeof(ops.GenParams)
     assert L.ppnet_sizeof_params(ctypes.c_int32(1)) == ctypes.sizeof(ops.PathParams)
+
+
+def test_new_entry_points_validate_before_touching_cuda():
+    import ctypes
+    from ppnet_b200 import _lib, ops
+    L = _lib.lib()
+    assert L.ppnet_path_synthesize(None, None) == -1 and b"null params" in L.ppnet_last_error()
+    p = ops.PathParams()
+    p.n_paths, p.seg_num, p.poly_order, p.hmax, p.pomax, p.max_obst_iter = 1, 65, 4, 64, 32, 8
+    p.resolution, p.map_size = 224.0, 50.0
+    assert L.ppnet_path_synthesize(ctypes.byref(p), None) == -1 and b"seg_num" in L.ppnet_last_error()
+    p.seg_num = 10
+    assert L.ppnet_path_synthesize(ctypes.byref(p), None) == -1 and b"output pointer" in L.ppnet_last_error()
+    p.n_paths = 0
+    assert L.ppnet_path_synthesize(ctypes.byref(p), None) == 0            # empty batch: no-op, nothing dereferenced
+    assert L.ppnet_mask_rigid(None, ctypes.c_int32(448), None, None, ctypes.c_int64(3), ctypes.c_int32(224), None, None) == -1
+    assert L.ppnet_add_init_end(None, ctypes.c_int32(224), None, None, ctypes.c_int64(0), None) == 0
+    assert L.ppnet_bits_to_image(None, ctypes.c_int32(224), ctypes.c_int64(2), None, None, None) == -1
+    assert L.ppnet_generate_and_check_host(None, None, None, None) == -1
+
+
+def test_mirror_modules_import_without_a_gpu_and_refuse_to_compute():
+    import pytest
+    from ppnet_b200 import PPNetError, edage, mpnet
+    from ppnet_b200.edage import GMM, MapGenerate, Path, PathGenerate, PathSeg, process_map   # noqa: F401
+    edage.seed(1)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(PPNetError):
+            Path.Path(seg_num=3)
+        with pytest.raises(PPNetError):
+            process_map.collision_check_circle_edge((1, 1), (2, 2), [], 4.48)
+        mpnet.obc = [[]]
+        with pytest.raises(PPNetError):
+            mpnet.steerTo([1.0, 1.0], [2.0, 2.0], 0)

@@ -211,3 +211,48 @@ def test_fused_host_call_equals_the_device_ops():
     assert hout["counters"][0] == M and hout["counters"][1] == int(hout["valid"].sum())
     h2d, d2h = ctx.bytes_moved()
     assert h2d == M * SPM * 48 and d2h > M * SPM * 3
+
+
+def test_next_rows_placement_label_masks_and_path_extraction(golden, tmp_path):
+    """N1-N3 against the real reference (tests/golden/masks.npz): corridor placement pixel-exact, label masks with the
+    same painted pixels, extract_path with the same waypoints / the same failures."""
+    from PIL import Image
+    from ppnet_b200 import ops
+    from ppnet_b200.edage import process_map
+    g = golden("masks")
+    n = len(g["n1_angle"])
+    space = torch.from_numpy(g["n1_space"]).cuda()
+    idx = torch.from_numpy(g["n1_path"]).long().cuda()
+    placed = ops.mask_rigid(space[idx].contiguous(), torch.from_numpy(-g["n1_angle"]).cuda(),
+                            torch.from_numpy(g["n1_translation"].astype(np.float64)).cuda(), 224)
+    assert np.array_equal(placed.cpu().numpy(), g["n1_placed"])                       # N1 (MapGenerate.py:102-106)
+    m = process_map.gen_path_masks(g["n2_pathpoint"])
+    assert np.array_equal(m.cpu().numpy() != 0, g["n2_gen_path"] != 0)               # N2a painted set
+    process_map.generate_gen_path(g["n2_pathpoint"], 0, root=str(tmp_path / "mask_path"))
+    for i in range(n):
+        assert np.array_equal(np.asarray(Image.open(tmp_path / "mask_path" / ("%d.png" % i))), g["n2_gen_path"][i])
+    pil_spaces = [Image.fromarray(np.stack([sp] * 3, axis=2)) for sp in g["n1_space"]]
+    process_map.generate_seg_space(pil_spaces, g["n2_pathpoint"], list(g["n1_angle"]), g["n1_translation"].tolist(), 0,
+                                   root=str(tmp_path / "mask_space"))
+    for i in range(n):
+        assert np.array_equal(np.asarray(Image.open(tmp_path / "mask_space" / ("%d.png" % i))), g["n2_seg_space"][i])
+    # N3: batched kernel and the reference-signature wrapper
+    K, ds = int(g["n3_count"]), int(g["n3_ds"])
+    masks = torch.from_numpy(np.stack([g["n3_%d_mask" % k] for k in range(K)])).cuda()
+    init = torch.from_numpy(np.stack([g["n3_%d_init" % k] for k in range(K)])).cuda()
+    end = torch.from_numpy(np.stack([g["n3_%d_end" % k] for k in range(K)])).cuda()
+    out, ln, ok = ops.extract_path(masks, init, end, float(ds), max_len=2048)
+    for k in range(K):
+        assert bool(ok[k].item()) == bool(g["n3_%d_ok" % k])
+        want = g["n3_%d_path" % k]
+        assert int(ln[k].item()) == len(want)
+        assert np.array_equal(out[k, :len(want)].cpu().numpy(), want)
+    assert ok.sum().item() >= 2 and (ok == 0).sum().item() >= 2
+    # ... and the verdicts extract_path_image would draw from it (process_map.py:491-495): batched == edge by edge
+    k0 = next(k for k in range(K) if bool(g["n3_%d_ok" % k]))
+    path = g["n3_%d_path" % k0]
+    obs = [[60.0, 60.0, 9.0], [150.0, 120.0, 14.0], [float(path[len(path) // 2][1]), float(path[len(path) // 2][0]), 3.0]]
+    v = process_map.collision_check_path(path, obs, C)
+    want_v = c_oracle.segcheck_f64(np.concatenate([path[:-1], path[1:]], axis=1), np.zeros(len(path) - 1, dtype=np.int32),
+                                   np.asarray(obs)[None], np.asarray([3], dtype=np.int32), C)
+    assert np.array_equal(v, want_v.astype(bool)) and v.any()

@@ -369,3 +369,17 @@ def test_space_normalization_isles_and_path_obstacles_vs_reference(golden):
         for x, y, r in obs:
             d = np.sqrt((odd[:, 0] - y) ** 2 + (odd[:, 1] - x) ** 2).min()
             assert d >= r + c / 50 * 224 - 1e-4          # radius is float32 when it was not clamped
+
+
+def test_next_rows_oracle_vs_reference(golden):
+    """N1 corridor placement, N2 label masks, N3 extract_path against tests/golden/masks.npz (real reference)."""
+    g = golden("masks")
+    for i in range(len(g["n1_angle"])):
+        placed = orc.mask_rigid(g["n1_space"][g["n1_path"][i]], -g["n1_angle"][i], g["n1_translation"][i], 224)
+        assert np.array_equal(placed, g["n1_placed"][i])
+        assert np.array_equal(orc.gen_path_mask(g["n2_pathpoint"][i]) != 0, g["n2_gen_path"][i] != 0)
+        assert np.array_equal(placed > 127, g["n2_seg_space"][i] != 0)
+    for k in range(int(g["n3_count"])):
+        ok, path = orc.extract_path_walk(g["n3_%d_mask" % k], g["n3_%d_init" % k], g["n3_%d_end" % k], int(g["n3_ds"]))
+        assert ok == bool(g["n3_%d_ok" % k])
+        assert np.array_equal(path, g["n3_%d_path" % k])
