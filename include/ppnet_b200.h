@@ -280,6 +280,12 @@ int ppnet_extract_path(const float* mask, int32_t h, int32_t w, const double* in
                        double down_sample_rate, int64_t n, int32_t max_len, double* out, int32_t* out_len, uint8_t* ok,
                        void* stream);
 
+/* N4  gerated_by_planners.generated_by_planners  EDaGe-PP/gerated_by_planners.py:88-157: the corridor and path label
+ *     masks of planner solutions.  wp[total][2] (x, y), solution i owns [path_off[i], path_off[i+1]) (max_len = the
+ *     longest); mask_space / mask_path [n][R][R] uint8 (row = y, col = x), 1 where the reference paints.            */
+int ppnet_planner_masks(const double* wp, const int64_t* path_off, int64_t n_paths, int64_t max_len, double clearance,
+                        int32_t resolution, int32_t points_per_seg, uint8_t* mask_space, uint8_t* mask_path, void* stream);
+
 /* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
 int ppnet_ctx_create(int32_t device, void** ctx);
 int ppnet_ctx_destroy(void* ctx);

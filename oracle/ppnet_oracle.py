@@ -802,6 +802,50 @@ def extract_path_walk(mask_small, init_state, end_state, down_sample_rate, max_s
 
 
 # --------------------------------------------------------------------------------------------
+# N4  gerated_by_planners.generated_by_planners, the two label masks (EDaGe-PP/gerated_by_planners.py:88-157)
+# --------------------------------------------------------------------------------------------
+def planner_masks(waypoints, clearance=1 / 50 * 224, resolution=224, points_per_seg=100):
+    """waypoints f64[L,2] (x, y) of one planner solution.  Returns (mask_space u8[R,R], mask_path u8[R,R]) in the
+    orientation of the saved files (row = y, col = x), non-zero where the reference paints."""
+    p = np.asarray(waypoints, dtype=np.float64)
+    R = resolution
+    step_img = 1 / 224                                             # hard-coded (:58)
+    K = round(clearance / 2 / step_img)
+    space = np.zeros([R, R], dtype=np.uint8)
+    pathm = np.zeros([R, R], dtype=np.uint8)
+
+    def paint(m, pts):
+        x = np.rint(pts[:, 0])
+        y = np.rint(pts[:, 1])
+        ok = (x > 0) & (x < R - 1) & (y > 0) & (y < R - 1)          # 0 < x < 223 and 0 < y < 223
+        m[y[ok].astype(int), x[ok].astype(int)] = 1
+
+    ks = (np.arange(K) * step_img)[:, None]
+    for a, b in ((p[0], p[-1]), (p[-1], p[0])):                    # 360 rays around each end point (:98-111)
+        d = a - b
+        d = d / np.sqrt(dot2_f64(d[0], d[1], d[0], d[1], DOT_FUSED_SKX))
+        for l in range(360):
+            rad = l / 180 * np.pi
+            c, s_ = np.cos(rad), np.sin(rad)
+            dl = np.array([c * d[0] + (-s_) * d[1], s_ * d[0] + c * d[1]])
+            paint(space, a + ks * dl)
+    wps = []
+    for l in range(len(p) - 1):                                    # +-normal band along every edge (:114-134)
+        d = p[l + 1] - p[l]
+        nd = np.sqrt(dot2_f64(d[0], d[1], d[0], d[1], DOT_FUSED_SKX))
+        d = d / nd
+        step = np.sqrt(f64((p[l][0] - p[l + 1][0]) ** 2 + (p[l][1] - p[l + 1][1]) ** 2)) / points_per_seg
+        nrm = np.array([d[1], -d[0]])
+        for j in range(points_per_seg):
+            w = p[l] + j * step * d
+            wps.append(w)
+            paint(space, w + ks * nrm)
+            paint(space, w - ks * nrm)
+    paint(pathm, np.asarray(wps).reshape(-1, 2))
+    return space, pathm
+
+
+# --------------------------------------------------------------------------------------------
 # A15  plot_obstacles -- GEOMETRIC restatement (parity UNPINNED: matplotlib/Agg/JPEG/PIL dither
 #      are not installed; see DESIGN.md).  Pixel (row i, col j) is obstacle iff its centre
 #      (j + 0.5, i + 0.5) lies inside a disk (x, y, r [+ inflate]).

@@ -6,6 +6,9 @@
 // (N1 / the mask half of N2 -- torchvision rotate + affine of a corridor mask -- is ppnet_mask_rigid in grid.cu.)
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 namespace ppnet {
@@ -87,9 +90,84 @@ extract_path_kernel(const float* __restrict__ mask, int h, int w, const double* 
     if (lane == 0) { out_len[m] = success ? L + 2 : 0; ok[m] = success ? 1 : 0; }
 }
 
+// N4  gerated_by_planners.generated_by_planners, the two label masks (EDaGe-PP/gerated_by_planners.py:88-157).
+// One thread per ray: 360 rays around each end point, then +-normal rays at 100 samples per edge; a ray is K sub-pixel
+// steps of 1/224 px (K = round(clearance / 2 * 224) = 502 at the reference's clearance).  Cells are stored in the
+// orientation of the saved files (row = y, col = x).
+__global__ void planner_mask_kernel(const double* __restrict__ wp, const int64_t* __restrict__ path_off, int K, int R,
+                                    int pps, uint8_t* __restrict__ space, uint8_t* __restrict__ pathm) {
+    const int64_t m = blockIdx.y;
+    const int64_t lo = path_off[m], L = path_off[m + 1] - lo;
+    if (L < 2) return;
+    const double2* p = reinterpret_cast<const double2*>(wp) + lo;
+    const int n_cap = 720, n_band = (int)(L - 1) * pps * 2;
+    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_cap + n_band) return;
+    const double step_img = 1.0 / 224.0;
+    double ox, oy, dx, dy;
+    if (ray < n_cap) {
+        const bool at_end = ray >= 360;
+        const int l = at_end ? ray - 360 : ray;
+        const double2 a = at_end ? p[L - 1] : p[0], b = at_end ? p[0] : p[L - 1];
+        double d0 = __dsub_rn(a.x, b.x), d1 = __dsub_rn(a.y, b.y);
+        const double nn = __dsqrt_rn(__fma_rn(d1, d1, __dmul_rn(d0, d0)));            // np.linalg.norm (ddot)
+        d0 = __ddiv_rn(d0, nn); d1 = __ddiv_rn(d1, nn);
+        const double rad = __dmul_rn(__ddiv_rn((double)l, 180.0), 3.14159265358979323846);
+        const double c = cos(rad), s = sin(rad);
+        ox = a.x; oy = a.y;
+        dx = __dadd_rn(__dmul_rn(c, d0), __dmul_rn(-s, d1));                          // coord_rotation (1-D np.dot)
+        dy = __dadd_rn(__dmul_rn(s, d0), __dmul_rn(c, d1));
+    } else {
+        const int t = ray - n_cap;
+        const int l = t / (2 * pps), j = (t % (2 * pps)) >> 1;
+        const bool neg = t & 1;
+        const double2 a = p[l], b = p[l + 1];
+        double d0 = __dsub_rn(b.x, a.x), d1 = __dsub_rn(b.y, a.y);
+        const double nn = __dsqrt_rn(__fma_rn(d1, d1, __dmul_rn(d0, d0)));
+        d0 = __ddiv_rn(d0, nn); d1 = __ddiv_rn(d1, nn);
+        const double ex = __dsub_rn(a.x, b.x), ey = __dsub_rn(a.y, b.y);
+        const double step = __ddiv_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey))), (double)pps);   // scipy euclidean / 100
+        const double js = __dmul_rn((double)j, step);
+        ox = __dadd_rn(a.x, __dmul_rn(js, d0)); oy = __dadd_rn(a.y, __dmul_rn(js, d1));  // waypoint j of the edge
+        if (!neg) {                                                                   // the waypoint itself -> mask_path (once)
+            const double x = rint(ox), y = rint(oy);
+            if (x > 0.0 && x < (double)(R - 1) && y > 0.0 && y < (double)(R - 1)) pathm[((size_t)m * R + (int)y) * R + (int)x] = 1;
+        }
+        dx = d1; dy = -d0;                                                            // dir = [dir[1], -dir[0]]
+        if (neg) { dx = -dx; dy = -dy; }
+    }
+    int px = -1, py = -1;
+    for (int k = 0; k < K; ++k) {
+        const double ks = __dmul_rn((double)k, step_img);
+        const double x = rint(__dadd_rn(ox, __dmul_rn(ks, dx))), y = rint(__dadd_rn(oy, __dmul_rn(ks, dy)));
+        if (x > 0.0 && x < (double)(R - 1) && y > 0.0 && y < (double)(R - 1)) {
+            const int ix = (int)x, iy = (int)y;
+            if (ix != px || iy != py) { space[((size_t)m * R + iy) * R + ix] = 1; px = ix; py = iy; }   // ~224 steps per cell
+        }
+    }
+}
+
 }  // namespace ppnet
 
 using namespace ppnet;
+
+extern "C" int ppnet_planner_masks(const double* wp, const int64_t* path_off, int64_t n_paths, int64_t max_len,
+                                   double clearance, int32_t resolution, int32_t points_per_seg, uint8_t* mask_space,
+                                   uint8_t* mask_path, void* stream) {
+    PPNET_REQUIRE(n_paths >= 0 && resolution > 1 && points_per_seg > 0 && max_len >= 0, "planner_masks: bad sizes");
+    if (n_paths == 0) return PPNET_OK;
+    PPNET_REQUIRE(wp && path_off && mask_space && mask_path, "planner_masks: null pointer");
+    PPNET_REQUIRE(n_paths <= 65535, "planner_masks: at most 65535 solutions per launch");
+    const size_t bytes = (size_t)n_paths * resolution * resolution;
+    PPNET_CUDA(cudaMemsetAsync(mask_space, 0, bytes, (cudaStream_t)stream));
+    PPNET_CUDA(cudaMemsetAsync(mask_path, 0, bytes, (cudaStream_t)stream));
+    const int K = (int)nearbyint(clearance / 2.0 / (1.0 / 224.0));                    // round(clearance / 2 / step_img)
+    const int64_t rays = 720 + std::max<int64_t>(max_len - 1, 0) * points_per_seg * 2;
+    dim3 grid((unsigned)((rays + 127) / 128), (unsigned)n_paths);
+    planner_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(wp, path_off, K, resolution, points_per_seg, mask_space, mask_path);
+    PPNET_LAUNCH_CHECK("planner_mask_kernel");
+    return PPNET_OK;
+}
 
 extern "C" int ppnet_path_mask(const double* pathpt, int32_t np, int64_t n_maps, int32_t stride, int32_t resolution,
                                uint8_t* out, void* stream) {

@@ -519,3 +519,18 @@ def extract_path(mask, init_state, end_state, down_sample_rate, max_len=4096):
                                    ctypes.c_double(down_sample_rate), ctypes.c_int64(n), ctypes.c_int32(max_len), _ptr(out),
                                    _ptr(ln), _ptr(ok), _stream()), "ppnet_extract_path")
     return out, ln, ok
+
+
+def planner_masks(wp, path_off, clearance=1 / 50 * 224, resolution=224, points_per_seg=100):
+    """N4 (EDaGe-PP/gerated_by_planners.py:88-157): wp f64[total,2] (x, y), CSR path_off i64[n+1]
+    -> (mask_space u8[n,R,R], mask_path u8[n,R,R]) in file orientation (row = y, col = x), 1 = painted."""
+    _need(wp, torch.float64, "wp")
+    _need(path_off, torch.int64, "path_off")
+    n = path_off.numel() - 1
+    longest = int((path_off[1:] - path_off[:-1]).max().item()) if n else 0
+    sp = torch.empty([n, resolution, resolution], dtype=torch.uint8, device=wp.device)
+    pm = torch.empty_like(sp)
+    check(lib().ppnet_planner_masks(_ptr(wp), _ptr(path_off), ctypes.c_int64(n), ctypes.c_int64(longest),
+                                    ctypes.c_double(clearance), ctypes.c_int32(resolution), ctypes.c_int32(points_per_seg),
+                                    _ptr(sp), _ptr(pm), _stream()), "ppnet_planner_masks")
+    return sp, pm

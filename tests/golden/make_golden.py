@@ -638,6 +638,47 @@ def gen_masks():
     print("masks.npz", n, "maps", k, "extract_path cases, ok:", [bool(out["n3_%d_ok" % j]) for j in range(k)])
 
 
+# ---------------------------------------------------------------------------------------------
+def gen_planner_masks():
+    """N4: gerated_by_planners.generated_by_planners (EDaGe-PP/gerated_by_planners.py:56-161) run unmodified on a
+    synthetic solved-problems file (OMPL itself is not available): mask_space / mask_path PNGs per solution."""
+    import importlib
+    from PIL import Image
+    from oracle.ref_loader import find_reference
+    mods = load_edage()
+    sys.path.insert(0, os.path.join(find_reference(), "EDaGe-PP"))
+    try:
+        gp = importlib.import_module("gerated_by_planners")
+    finally:
+        sys.path.pop(0)
+    gp.imgviz.label_colormap = lambda: (np.arange(768) % 251).astype(np.uint8).reshape(256, 3)
+    rng = np.random.default_rng(31)
+    sols = []
+    for L in (2, 3, 5):
+        a, b = rng.uniform(20, 60, 2), rng.uniform(150, 205, 2)
+        t = np.linspace(0, 1, L)[:, None]
+        w = a + t * (b - a) + np.concatenate([[[0, 0]], rng.normal(0, 12, (L - 2, 2)), [[0, 0]]]) if L > 2 else a + t * (b - a)
+        sols.append(w)
+    sols.append(np.asarray([[3.2, 100.7], [120.4, 221.9], [222.6, 40.1]]))          # touches the borders
+    tmp = tempfile.mkdtemp(prefix="ppnet_golden_")
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    with open("solved.txt", "w") as f:
+        for w in sols:
+            prob = {"Obstacles": [[50.0, 60.0, 8.0]],
+                    "Solution": [{"Planner": "BITstar", "Waypoint": [[float(x), float(y)] for x, y in w], "Time": 1.0}]}
+            f.write(json.dumps(prob) + "\n")
+    with quiet():
+        gp.generated_by_planners("solved.txt")
+    out = {"n": len(sols), "wp": np.concatenate(sols), "off": np.cumsum([0] + [len(w) for w in sols]).astype(np.int64)}
+    out["mask_space"] = np.asarray([np.asarray(Image.open("data_BITstar/mask_space/%d.png" % i)) for i in range(len(sols))])
+    out["mask_path"] = np.asarray([np.asarray(Image.open("data_BITstar/mask_path/%d.png" % i)) for i in range(len(sols))])
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "planner_masks.npz"), **out)
+    print("planner_masks.npz", len(sols), "solutions; space px", [(m != 0).sum() for m in out["mask_space"]],
+          "path px", [(m != 0).sum() for m in out["mask_path"]], "values", np.unique(out["mask_space"]), np.unique(out["mask_path"]))
+
+
 GENS = {
     "segcheck_f64": lambda: gen_segcheck("f64", "segcheck_f64.npz"),
     "segcheck_f32": lambda: gen_segcheck("f32", "segcheck_f32.npz"),
@@ -646,6 +687,7 @@ GENS = {
     "mapgen": gen_mapgen,
     "misc": gen_misc,
     "masks": gen_masks,
+    "planner_masks": gen_planner_masks,
 }
 
 if __name__ == "__main__":

@@ -256,3 +256,35 @@ def test_next_rows_placement_label_masks_and_path_extraction(golden, tmp_path):
     want_v = c_oracle.segcheck_f64(np.concatenate([path[:-1], path[1:]], axis=1), np.zeros(len(path) - 1, dtype=np.int32),
                                    np.asarray(obs)[None], np.asarray([3], dtype=np.int32), C)
     assert np.array_equal(v, want_v.astype(bool)) and v.any()
+
+
+def test_planner_solution_masks_vs_reference(golden):
+    """N4: the corridor / path label masks of planner solutions == the PNGs the real generated_by_planners wrote."""
+    from ppnet_b200 import ops
+    g = golden("planner_masks")
+    sp, pm = ops.planner_masks(torch.from_numpy(g["wp"]).cuda(), torch.from_numpy(g["off"]).cuda())
+    assert np.array_equal(sp.cpu().numpy() != 0, g["mask_space"] != 0)
+    assert np.array_equal(pm.cpu().numpy() != 0, g["mask_path"] != 0)
+
+
+def test_generated_by_planners_mirror_writes_the_reference_files(golden, tmp_path):
+    from PIL import Image
+    from ppnet_b200.edage import gerated_by_planners as gp
+    g = golden("planner_masks")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with open("solved.txt", "w") as f:
+            for i in range(int(g["n"])):
+                w = g["wp"][g["off"][i]:g["off"][i + 1]]
+                f.write(json.dumps({"Obstacles": [[50.0, 60.0, 8.0]], "Solution": [
+                    {"Planner": "BITstar", "Waypoint": w.tolist(), "Time": 1.0},
+                    {"Planner": "RRTstar", "Waypoint": w.tolist(), "Time": 60.0}]}) + "\n")
+        gp.generated_by_planners("solved.txt")
+        for i in range(int(g["n"])):
+            assert np.array_equal(np.asarray(Image.open("data_BITstar/mask_space/%d.png" % i)), g["mask_space"][i])
+            assert np.array_equal(np.asarray(Image.open("data_BITstar/mask_path/%d.png" % i)), g["mask_path"][i])
+            assert os.path.exists("data_BITstar/map/%d.jpg" % i)
+        assert os.listdir("data_RRTstar/mask_path") == []                  # Time >= 59 is filtered out
+    finally:
+        os.chdir(cwd)

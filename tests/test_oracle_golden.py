@@ -383,3 +383,10 @@ def test_next_rows_oracle_vs_reference(golden):
         ok, path = orc.extract_path_walk(g["n3_%d_mask" % k], g["n3_%d_init" % k], g["n3_%d_end" % k], int(g["n3_ds"]))
         assert ok == bool(g["n3_%d_ok" % k])
         assert np.array_equal(path, g["n3_%d_path" % k])
+
+
+def test_planner_masks_oracle_vs_reference(golden):
+    g = golden("planner_masks")
+    for i in range(int(g["n"])):
+        sp, pm = orc.planner_masks(g["wp"][g["off"][i]:g["off"][i + 1]])
+        assert np.array_equal(sp != 0, g["mask_space"][i] != 0) and np.array_equal(pm != 0, g["mask_path"][i] != 0)
