@@ -147,7 +147,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_maps = 256
+    sample_maps = 2048
     for _ in range(max(args.warmup, 1)):
         cpu_baseline(32, threads, python_port_segments=50)
     t0 = time.perf_counter()
@@ -424,7 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--maps", type=int, default=10000, help="maps per GPU per step")
-    ap.add_argument("--cpu-sample-maps", type=int, default=512)
+    ap.add_argument("--cpu-sample-maps", type=int, default=4096, help="maps in the cpu_baseline sample (~10 core-seconds of C oracle work)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -131,7 +131,7 @@ __device__ __forceinline__ Circle<T> make_circle(const double* __restrict__ o, d
 }
 
 constexpr int kCircTile = 128;       // circles staged per pass (one bit each in a 128-bit candidate mask)
-constexpr int kSegThreads = 256;
+constexpr int kSegThreads = 128;
 
 // ---- the fast path: exact-safe culling + division-free decisions ----------------------------------------
 // Notation: u = unit roundoff of the flavour, Mg = |s|_1 + |e|_1 + |o|_1 + thr + 1 (bounds every length in
@@ -268,7 +268,7 @@ struct __align__(16) SegSlot {                   // what a pair needs of its seg
 };
 
 template <typename T, int MODE, bool SWAP, bool STEER>
-__global__ void __launch_bounds__(kSegThreads, 4)
+__global__ void __launch_bounds__(kSegThreads, 8)
 segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
                 const double* __restrict__ obs, const int32_t* __restrict__ obs_cnt, int omax,
                 double clearance, T bound, uint8_t* __restrict__ verdict, uint8_t* __restrict__ steer) {
