@@ -69,7 +69,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
     const uint32_t bytes = (uint32_t)(R * W * 4);
     int4* stage = reinterpret_cast<int4*>(dsm + 16 + ((bytes + 15u) & ~15u));   // walk records of the parked segments
     uint16_t* sidx = reinterpret_cast<uint16_t*>(stage + kDdaStage);           // their slot in the stage's result array
-    int16_t* res = reinterpret_cast<int16_t*>(sidx + kDdaStage);                // first blocked step per segment, -1 free
+    int32_t* res = reinterpret_cast<int32_t*>(sidx + kDdaStage);                // first blocked step per segment, -1 free
     const bool bulk = (bytes & 15u) == 0;
 
     if (bulk) {
@@ -130,7 +130,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
             int r0 = blocked0 ? 0 : (n == 0 ? -1 : -2);                    // -2: needs a walk
             if (r0 == -2 && n > kLaneWalkMaxN) r0 = walk_slow(bm, R, W, x0, y0, dx, dy);
             const bool walk = have && r0 == -2;
-            if (have && r0 != -2) res[t] = (int16_t)r0;
+            if (have && r0 != -2) res[t] = r0;
             // compaction of the survivors: ballot scan inside the warp, one shared atomic per warp
             const unsigned wm = __ballot_sync(0xffffffffu, walk);
             int wb = 0;
@@ -152,8 +152,10 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
         const int np_ = *parked;
 
         // ---- 2. walk: lanes pull parked segments until the stage is empty -----------------------------------
-        bool live = false, exhausted = np_ == 0, exitM = false;
-        int slot = 0, k = 0, kend = 0, a = 0, r = 0, n2 = 0, dm2 = 0, stepM = 0, stepm = 0, cm = 0;
+        bool live = false, exhausted = np_ == 0;
+        int32_t* res_ptr = res;                                            // where this lane's current segment reports
+        int res_end = -1;                                                  // its result if the walk reaches kend unblocked
+        int k = 0, kend = 0, a = 0, r = 0, n2 = 0, dm2 = 0, stepM = 0, stepm = 0, cm = 0;
         int wnext = 0, wend = 0;                                           // this warp's claimed range (warp-uniform)
         for (;;) {
             const unsigned need = __ballot_sync(0xffffffffu, !live);
@@ -172,7 +174,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
                     const int my = wnext + __popc(need & lt);
                     if (!live && my < wend) {
                         const int4 q = stage[my];
-                        slot = sidx[my];
+                        res_ptr = res + sidx[my];
                         const unsigned flags = (unsigned)q.x >> 28;
                         a = q.x & 0x0fffffff;
                         kend = q.y & 0xffff;
@@ -182,7 +184,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
                         r = n2 >> 1;
                         stepM = ((flags & 2u) ? 1 : -1) * ((flags & 1u) ? 1 : RS);
                         stepm = (flags & 1u) ? RS : 1;
-                        exitM = flags & 4u;
+                        res_end = (flags & 4u) ? kend + 1 : -1;    // next cell leaves by the major axis (blocked there) / end reached (free)
                         k = 0;
                         live = true;
                     }
@@ -200,8 +202,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
                 if (in) word = bm[a >> 5];
                 const bool blocked = (word >> (a & 31)) & 1u;              // occupied, or outside by the minor axis
                 const bool done = live && (blocked || k == kend);
-                // at kend and free: the next cell leaves by the major axis (blocked at k+1) or the end was reached (free)
-                if (done) res[slot] = (int16_t)(blocked ? k : (exitM ? k + 1 : -1));
+                if (done) *res_ptr = blocked ? k : res_end;
                 live = live && !done;
                 ++k;                                                       // (a finished lane's state is dead; advancing it is harmless)
                 a += stepM;
@@ -239,7 +240,7 @@ extern "C" int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int
     const size_t bm_bytes = (size_t)resolution * W * 4;
     PPNET_REQUIRE((reinterpret_cast<uintptr_t>(bits) & 15) == 0 && (reinterpret_cast<uintptr_t>(segs_xy) & 15) == 0,
                   "dda: bits and segs must be 16-byte aligned");
-    const size_t smem = ((bm_bytes + 15) & ~(size_t)15) + 16 + (size_t)kDdaStage * (16 + 2 + 2);
+    const size_t smem = ((bm_bytes + 15) & ~(size_t)15) + 16 + (size_t)kDdaStage * (16 + 2 + 4);
     PPNET_REQUIRE(smem <= 220 * 1024, "dda: resolution too large for a shared-memory bitmap");
     // big bitmaps: amortise the staging over every segment of the map; small ones: more CTAs in flight
     const int chunk = bm_bytes >= 64 * 1024 ? 8192 : kDdaStage;
