@@ -141,10 +141,10 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
                 const int dM = xmaj ? dx : dy, cM = xmaj ? x0 : y0;
                 const int kM = dM > 0 ? R - cM : cM + 1;                   // first k whose major coordinate is outside
                 const int kend = min(n, kM - 1);
-                const unsigned flags = (xmaj ? 1u : 0u) | (dM > 0 ? 2u : 0u) | (kM - 1 < n ? 4u : 0u);
+                const int dm = xmaj ? dy : dx;                             // minor-axis delta, |dm| <= n
+                const unsigned flags = (xmaj ? 1u : 0u) | (dM > 0 ? 2u : 0u) | (kM - 1 < n ? 4u : 0u) | (dm < 0 ? 8u : 0u);
                 const int pos = wb + __popc(wm & lt);
-                stage[pos] = make_int4((int)((unsigned)a | (flags << 28)), kend | ((xmaj ? y0 : x0) << 16),
-                                       2 * (xmaj ? dy : dx), 2 * n);
+                stage[pos] = make_int4((int)((unsigned)a | (flags << 28)), kend | ((xmaj ? y0 : x0) << 16), 2 * abs(dm), 2 * n);
                 sidx[pos] = (uint16_t)t;
             }
         }
@@ -155,7 +155,8 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
         bool live = false, exhausted = np_ == 0;
         int32_t* res_ptr = res;                                            // where this lane's current segment reports
         int res_end = -1;                                                  // its result if the walk reaches kend unblocked
-        int k = 0, kend = 0, a = 0, r = 0, n2 = 0, dm2 = 0, stepM = 0, stepm = 0, cm = 0;
+        int k = 0, kend = 0, a = 0, r = 0, n2 = 0, inc = 0, stepM = 0, stepm = 0, stepc = 0, cm = 0;
+        const uint32_t bm_s = smem_u32(bm);
         int wnext = 0, wend = 0;                                           // this warp's claimed range (warp-uniform)
         for (;;) {
             const unsigned need = __ballot_sync(0xffffffffu, !live);
@@ -179,11 +180,14 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
                         a = q.x & 0x0fffffff;
                         kend = q.y & 0xffff;
                         cm = q.y >> 16;
-                        dm2 = q.z;
+                        inc = q.z;                                 // 2 |d_minor|
                         n2 = q.w;
-                        r = n2 >> 1;
+                        // remainder of (2 k d_minor + n) mod 2n, kept as a count-up for either sign: for d_minor < 0 the
+                        // mirrored remainder 2n - 1 - r starts at n - 1 and wraps exactly when r would drop below 0
+                        r = (n2 >> 1) - ((flags & 8u) ? 1 : 0);
                         stepM = ((flags & 2u) ? 1 : -1) * ((flags & 1u) ? 1 : RS);
-                        stepm = (flags & 1u) ? RS : 1;
+                        stepm = ((flags & 8u) ? -1 : 1) * ((flags & 1u) ? RS : 1);
+                        stepc = (flags & 8u) ? -1 : 1;
                         res_end = (flags & 4u) ? kend + 1 : -1;    // next cell leaves by the major axis (blocked there) / end reached (free)
                         k = 0;
                         live = true;
@@ -199,18 +203,17 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
             for (int u = 0; u < 4; ++u) {                                  // 4 cells between two warp votes; straight-line code
                 const bool in = live && (unsigned)cm < (unsigned)R;       // minor coordinate still inside?
                 uint32_t word = 0xffffffffu;
-                if (in) word = bm[a >> 5];
+                if (in) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bm_s + ((uint32_t)(a >> 5) << 2)));
                 const bool blocked = (word >> (a & 31)) & 1u;              // occupied, or outside by the minor axis
                 const bool done = live && (blocked || k == kend);
                 if (done) *res_ptr = blocked ? k : res_end;
                 live = live && !done;
                 ++k;                                                       // (a finished lane's state is dead; advancing it is harmless)
-                a += stepM;
-                r += dm2;
-                const bool up = r >= n2, dn = r < 0;
-                r += (dn ? n2 : 0) - (up ? n2 : 0);
-                a += (up ? stepm : 0) - (dn ? stepm : 0);
-                cm += (int)up - (int)dn;
+                r += inc;
+                const bool wrap = r >= n2;                                 // the minor axis moves one cell
+                r -= wrap ? n2 : 0;
+                a += stepM + (wrap ? stepm : 0);
+                cm += wrap ? stepc : 0;
             }
         }
         __syncthreads();
