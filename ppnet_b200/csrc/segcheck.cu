@@ -367,7 +367,7 @@ segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, 
                     const float sx = (float)q.s0 * bscale, sy = (float)q.s1 * bscale;
                     const float dx = (float)q.d0 * bscale, dy = (float)q.d1 * bscale;
                     const float mb = (float)q.es * bscale + 2e-3f;
-                    const int np_ = min(16, 1 + (int)(fmaxf(fabsf(dx), fabsf(dy)) * (1.0f / 3.0f)));
+                    const int np_ = min(16, 1 + (int)(fmaxf(fabsf(dx), fabsf(dy)) * (1.0f / 12.0f)));
                     const float inv = 1.0f / (float)np_;
                     uint32_t n0 = ~0u, n1 = ~0u, n2 = ~0u, n3 = ~0u;       // circles culled by EVERY piece
                     for (int pc = 0; pc < np_; ++pc) {
