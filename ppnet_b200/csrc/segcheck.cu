@@ -303,9 +303,9 @@ segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, 
         const int nt = max(0, min(kCircTile, cnt - t0));
         const bool first_tile = t0 == 0, last_tile = t0 + kCircTile >= cnt;
         __syncthreads();
-        if (threadIdx.x < 4 * kBins) {
+        for (int t = threadIdx.x; t < 4 * kBins; t += kSegThreads) {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            (threadIdx.x < 2 * kBins ? &edge_lo[0][0] : &edge_hi[0][0] - 2 * kBins)[threadIdx.x] = z;
+            (t < 2 * kBins ? &edge_lo[0][0] : &edge_hi[0][0] - 2 * kBins)[t] = z;
         }
         if (threadIdx.x < 4) { live_mask[threadIdx.x] = 0u; odd_mask[threadIdx.x] = 0u; }
         __syncthreads();
@@ -334,8 +334,8 @@ segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, 
             }
         }
         __syncthreads();
-        if (threadIdx.x < 4 * kBins) {            // prefix tables: (axis, which, bin) per thread
-            const int axis = (threadIdx.x >> 5) & 1, which = threadIdx.x >> 6, bin = threadIdx.x & 31;
+        for (int t = threadIdx.x; t < 4 * kBins; t += kSegThreads) {   // prefix tables: one (which, axis, bin) entry per thread
+            const int bin = t % kBins, axis = (t / kBins) & 1, which = t / (2 * kBins);
             uint4 acc = make_uint4(0u, 0u, 0u, 0u);
             if (which == 0) {
                 for (int b = 0; b < bin; ++b) { const uint4 t = edge_hi[axis][b]; acc.x |= t.x; acc.y |= t.y; acc.z |= t.z; acc.w |= t.w; }
