@@ -262,13 +262,19 @@ constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kQueueCap = 512;                   // pairs per round (16 per lane)
 constexpr int kTakeMax = kQueueCap / 32;
 
+// resident CTAs per SM the compiler must allow: f64 needs its 80 registers (spills cost more than occupancy gives),
+// f32 is better off at 64 registers and 8 CTAs (measured)
+template <typename T> struct SegOcc;
+template <> struct SegOcc<double> { static constexpr int kMinBlocks = 6; };
+template <> struct SegOcc<float> { static constexpr int kMinBlocks = 8; };
+
 template <typename T>
 struct __align__(16) SegSlot {                   // what a pair needs of its segment (d, |d|^2 are recomputed)
     T s0, s1, e0, e1, L, es;                     // L == 0 marks a verbatim-only segment
 };
 
 template <typename T, int MODE, bool SWAP, bool STEER>
-__global__ void __launch_bounds__(kSegThreads, 8)
+__global__ void __launch_bounds__(kSegThreads, SegOcc<T>::kMinBlocks)
 segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
                 const double* __restrict__ obs, const int32_t* __restrict__ obs_cnt, int omax,
                 double clearance, T bound, uint8_t* __restrict__ verdict, uint8_t* __restrict__ steer) {
