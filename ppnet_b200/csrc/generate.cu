@@ -11,7 +11,8 @@
 //      `while` of the reference).  In parity mode the draws come from the caller instead.
 //   2. all threads rotate/translate the 1000 path points + 11 segment points (label, 16.2 KB -- the
 //      dominant HBM stream, written with 16-byte stores) and keep the odd-indexed points in shared memory.
-//   3. candidate circles: thread k draws candidate k once.  The staged odd points are grouped into boxes of 16
+//   3. candidate circles: drawn (Philox, one thread per candidate) by warps 1.. while warp 0 is busy with step 1.
+//      The staged odd points are grouped into boxes of 16
 //      consecutive points; the (candidate, box) pairs are spread over the CTA (warp = candidate, lane = box,
 //      no cross-lane reduction): a pair is skipped when the
 //      candidate is farther from the box than the threshold plus a 1e7-ulp margin (those points cannot be the
@@ -142,10 +143,34 @@ generate_kernel(ppnet_gen_params P) {
 
     for (int i = threadIdx.x; i < H; i += kGenThreads)
         hull[i] = reinterpret_cast<const double2*>(P.bank_hull)[(size_t)j * P.hmax + i];
-    for (int i = threadIdx.x; i < words; i += kGenThreads) bm[i] = 0u;
     __syncthreads();
+    const double M = P.map_size;
+    const double thr_c = __dmul_rn(__ddiv_rn(P.clearance, M), R);             // c / M * R
 
     // ---- 1. placement: rejection loop, 32 tries per round (first passing try wins) -------------------
+    //         ... while the other warps draw the candidate circles (neither depends on the other) and clear the bitmap
+    if (warp != 0) {
+        for (int i = threadIdx.x - 32; i < words; i += kGenThreads - 32) bm[i] = 0u;
+        for (int k = threadIdx.x - 32; k < O; k += kGenThreads - 32) {        // one Philox draw per candidate (:128-130)
+            double x, y, r;
+            if (P.in_cand) {
+                const double* c = P.in_cand + ((size_t)lm * O + k) * 3;
+                x = c[0]; y = c[1]; r = c[2];
+            } else {
+                draw_candidate(key, g, k, O, M, P.obstacle_size, x, y, r);
+            }
+            double* o = sobs + 3 * k;                      // [coord_img[1], coord_img[0], radius_img]  (:134-136, :143)
+            const double q1 = __dmul_rn(__ddiv_rn(y, M), R), q0 = __dmul_rn(__ddiv_rn(x, M), R);
+            const double rimg = __dmul_rn(__ddiv_rn(r, M), R);
+            o[0] = q1; o[1] = q0; o[2] = rimg;
+            const double thr = __dadd_rn(rimg, thr_c);
+            // squared cull radius: (thr + margin)^2 with the margin ~1e7 ulp of the coordinates involved
+            const double cr = thr + 1e-9 * (R + fabs(q0) + fabs(q1) + fabs(thr));
+            thr_s[k] = thr;
+            cull_s[k] = cr * cr * (1.0 + 1e-12);
+            m2_s[k] = 0x7ff0000000000000ull;               // +inf
+        }
+    }
     if (warp == 0) {
         int tries = 0;
         double angle = 0.0;
@@ -230,9 +255,7 @@ generate_kernel(ppnet_gen_params P) {
     }
     __syncthreads();
 
-    // ---- 3. candidate circles: draws + clearance verdict (MapGenerate.py:128-143) ----------------------
-    const double M = P.map_size;
-    const double thr_c = __dmul_rn(__ddiv_rn(P.clearance, M), R);             // c / M * R
+    // ---- 3. candidate circles: clearance verdict (MapGenerate.py:132-143) --------------------------------
     for (int b = threadIdx.x; b < n_blk; b += kGenThreads) {                  // boxes of the staged odd points
         double4 bb = make_double4(CUDART_INF, -CUDART_INF, CUDART_INF, -CUDART_INF);
         const int e = min(n_odd, (b + 1) * kBlkPts);
@@ -242,27 +265,8 @@ generate_kernel(ppnet_gen_params P) {
         }
         box[b] = bb;
     }
-    for (int k = threadIdx.x; k < O; k += kGenThreads) {                      // one Philox draw per candidate
-        double x, y, r;
-        if (P.in_cand) {
-            const double* c = P.in_cand + ((size_t)lm * O + k) * 3;
-            x = c[0]; y = c[1]; r = c[2];
-        } else {
-            draw_candidate(key, g, k, O, M, P.obstacle_size, x, y, r);
-        }
-        double* o = sobs + 3 * k;                          // [coord_img[1], coord_img[0], radius_img]  (:134-136, :143)
-        const double q1 = __dmul_rn(__ddiv_rn(y, M), R), q0 = __dmul_rn(__ddiv_rn(x, M), R);
-        const double rimg = __dmul_rn(__ddiv_rn(r, M), R);
-        o[0] = q1; o[1] = q0; o[2] = rimg;
-        const double thr = __dadd_rn(rimg, thr_c);
-        // squared cull radius: (thr + margin)^2 with the margin ~1e7 ulp of the coordinates involved
-        const double cr = thr + 1e-9 * (R + fabs(q0) + fabs(q1) + fabs(thr));
-        thr_s[k] = thr;
-        cull_s[k] = cr * cr * (1.0 + 1e-12);
-        m2_s[k] = 0x7ff0000000000000ull;                   // +inf
-    }
     __syncthreads();
-    // flat (candidate, box) pairs over the whole CTA: a pair whose box is farther than the cull radius cannot hold
+    // (candidate, box) pairs over the whole CTA: a pair whose box is farther than the cull radius cannot hold
     // the point that decides `min(dis) > r_px + c_px`; the others evaluate their 16 points with the reference's
     // un-fused arithmetic and fold into the candidate's minimum with one shared-memory atomicMin.
     for (int k = warp; k < O; k += kGenWarps) {            // warp <-> candidate, lane <-> box: no index arithmetic
@@ -282,18 +286,15 @@ generate_kernel(ppnet_gen_params P) {
         }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < O; k += kGenThreads) {
-        // sqrt is monotone: sqrt(min d^2) == min sqrt(d^2); skipped boxes only hold points with d > thr
-        acc_s[k] = __dsqrt_rn(__longlong_as_double((long long)m2_s[k])) > thr_s[k] ? 1 : 0;   // :142
-    }
-    __syncthreads();
-    // ordered compaction of the accepted candidates (the reference appends in loop order)
+    // verdict + ordered compaction of the accepted candidates (the reference appends in loop order)
     if (warp == 0) {
         int base = 0;
         double* gout = P.out_obs ? P.out_obs + (size_t)lm * omax_out * 3 : nullptr;
         for (int k0 = 0; k0 < O; k0 += 32) {
             const int k = k0 + lane;
-            const bool ok = k < O && acc_s[k];
+            // sqrt is monotone: sqrt(min d^2) == min sqrt(d^2); skipped boxes only hold points with d > thr   (:142)
+            const bool ok = k < O && __dsqrt_rn(__longlong_as_double((long long)m2_s[k])) > thr_s[k];
+            if (k < O) acc_s[k] = ok ? 1 : 0;
             const unsigned bal = __ballot_sync(0xffffffffu, ok);
             if (ok && gout) {
                 const int d = base + __popc(bal & ((1u << lane) - 1));
