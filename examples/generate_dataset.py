@@ -43,6 +43,8 @@ def main():
                                round_index=round_index, write_problems=bool(args.out), save_images=args.images)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
+        if args.out and args.images:                               # MapGenerate.py:174: the label file SegNet / GenNet loaders read
+            torch.save(map_generator.MapLabel, '{}/data/MapLabel'.format(os.path.join(args.out, str(round_index))))
         if round_index:
             times.append((t1 - t0, t2 - t1))
             labels += len(map_generator.MapLabel)

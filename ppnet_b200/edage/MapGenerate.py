@@ -94,6 +94,9 @@ class MapGenerate:
     def save_images(self, folder_path):
         import torchvision
         os.makedirs(os.path.join(folder_path, 'data'), exist_ok=True)
+        os.makedirs(os.path.join(folder_path, 'GMM'), exist_ok=True)         # created (and left empty) by the reference too
+        for j, tp in enumerate(self.PathGroup.TargetPaths):                  # MapGenerate.py:56
+            torchvision.utils.save_image(tp.Space, r'{}/data/{}.jpg'.format(folder_path, j))
         imgs = self.map_images()
         for g in range(imgs.shape[0]):
             torchvision.utils.save_image(imgs[g], r'{}/{}.jpg'.format(folder_path, g))
