@@ -407,13 +407,21 @@ segcheck_kernel(const T* __restrict__ pts, const int64_t* __restrict__ seg_off, 
                 const int total = __shfl_sync(0xffffffffu, off, 31);
                 off -= mine;
                 __syncwarp();
-                for (int t = 0; t < mine; ++t) {
-                    int j;
-                    if (c0) { const int b = __ffs(c0) - 1; c0 &= c0 - 1; j = b; }
-                    else if (c1) { const int b = __ffs(c1) - 1; c1 &= c1 - 1; j = 32 + b; }
-                    else if (c2) { const int b = __ffs(c2) - 1; c2 &= c2 - 1; j = 64 + b; }
-                    else { const int b = __ffs(c3) - 1; c3 &= c3 - 1; j = 96 + b; }
-                    queue[warp][off + t] = (uint16_t)((lane << 8) | j);
+                {   // one short loop per mask word (simple body) instead of one loop choosing the word every time
+                    uint16_t* qp = &queue[warp][off];
+                    const uint16_t tag = (uint16_t)(lane << 8);
+                    int room = mine;
+#define PPNET_DRAIN(cw, basej)                                                                  \
+                    for (int t = min(room, __popc(cw)); t > 0; --t, --room) {                   \
+                        const int b = __ffs(cw) - 1;                                            \
+                        cw &= cw - 1;                                                           \
+                        *qp++ = (uint16_t)(tag | (basej + b));                                  \
+                    }
+                    PPNET_DRAIN(c0, 0)
+                    PPNET_DRAIN(c1, 32)
+                    PPNET_DRAIN(c2, 64)
+                    PPNET_DRAIN(c3, 96)
+#undef PPNET_DRAIN
                 }
                 __syncwarp();
                 for (int k = lane; k < total; k += 32) {
