@@ -90,7 +90,7 @@ def gmm_params(seed, order, dim, mean_range, std_range):
 
 def gmm_sample(seed, sample0, n, mean, std, w):
     """dim <= 2 layout: block 0 of sample i: x -> component, (y, z) -> Box-Muller pair (float32 math;
-    the device uses logf / sincospif, so values agree to ~1e-5 relative, components exactly)."""
+    the device uses the SFU __logf / __sincosf, so values agree to ~1e-4 absolute, components exactly)."""
     K, D = mean.shape
     assert D <= 2
     r = philox4x32_10(key_of(seed), _ctr(np.zeros(n), STREAM_GMM_SAMPLE, sample0 + np.arange(n, dtype=np.uint64)))

@@ -78,9 +78,13 @@ gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const fl
         // Box-Muller on (0,1] x [0,1): u1 = (wa + 1) / 2^32 never 0
         const float u1 = ((float)(wa >> 8) + 1.0f) * (1.0f / 16777216.0f);
         const float u2 = u24(wb);
-        const float rad = sqrtf(-2.0f * logf(u1));
+        // SFU transcendentals (MUFU.LG2 / SIN / COS, |error| ~ 2^-21): sampling parity is statistical, and the argument of
+        // sin / cos is folded into [-pi, pi) where the hardware approximations are at their best:
+        // cos(2 pi u) = -cos(2 pi u - pi), sin(2 pi u) = -sin(2 pi u - pi)
+        const float rad = sqrtf(-2.0f * __logf(u1));
         float sn, cs;
-        sincospif(2.0f * u2, &sn, &cs);
+        __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);
+        sn = -sn; cs = -cs;
         const float m0 = cache ? s_mean[k * D + d] : mean[k * D + d];
         const float s0 = cache ? s_std[k * D + d] : stdv[k * D + d];
         out[i * D + d] = m0 + s0 * (rad * cs);
