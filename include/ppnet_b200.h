@@ -286,6 +286,13 @@ int ppnet_extract_path(const float* mask, int32_t h, int32_t w, const double* in
 int ppnet_planner_masks(const double* wp, const int64_t* path_off, int64_t n_paths, int64_t max_len, double clearance,
                         int32_t resolution, int32_t points_per_seg, uint8_t* mask_space, uint8_t* mask_path, void* stream);
 
+/* ---- ordered stream compaction of the survivors of a verdict array (free segments, feasible paths ...):
+ *      out_idx[0 .. *out_count) = ascending i with flags[i] == keep.  workspace: ppnet_compact_workspace_elems(n)
+ *      int64 elements of device memory (per-CTA counts; no hidden allocation).                                     */
+int64_t ppnet_compact_workspace_elems(int64_t n);
+int ppnet_compact_u8(const uint8_t* flags, int64_t n, uint8_t keep, int64_t* out_idx, int64_t* out_count,
+                     int64_t* workspace, void* stream);
+
 /* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
 int ppnet_ctx_create(int32_t device, void** ctx);
 int ppnet_ctx_destroy(void* ctx);

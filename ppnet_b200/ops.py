@@ -534,3 +534,18 @@ def planner_masks(wp, path_off, clearance=1 / 50 * 224, resolution=224, points_p
                                     ctypes.c_double(clearance), ctypes.c_int32(resolution), ctypes.c_int32(points_per_seg),
                                     _ptr(sp), _ptr(pm), _stream()), "ppnet_planner_masks")
     return sp, pm
+
+
+def compact_u8(flags, keep=0):
+    """Ordered stream compaction: indices i (ascending) with flags[i] == keep -> (idx i64[n] (first `count` valid),
+    count i64[1]) on the device, e.g. the free segments of a verdict array or the feasible paths."""
+    _need(flags, torch.uint8, "flags")
+    n = flags.numel()
+    L = lib()
+    L.ppnet_compact_workspace_elems.restype = ctypes.c_int64
+    ws = torch.empty([int(L.ppnet_compact_workspace_elems(ctypes.c_int64(n)))], dtype=torch.int64, device=flags.device)
+    idx = torch.empty([n], dtype=torch.int64, device=flags.device)
+    cnt = torch.empty([1], dtype=torch.int64, device=flags.device)
+    check(L.ppnet_compact_u8(_ptr(flags), ctypes.c_int64(n), ctypes.c_uint8(keep), _ptr(idx), _ptr(cnt), _ptr(ws), _stream()),
+          "ppnet_compact_u8")
+    return idx, cnt

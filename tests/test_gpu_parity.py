@@ -337,3 +337,17 @@ def test_corridor_paint_golden(ops, golden):
                             448, 448).cpu().numpy()
     for k in range(len(wants)):
         assert np.array_equal(sp[k], wants[k]), k
+
+
+def test_compact_survivors(ops):
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 31, 1024, 1025, 3_000_001):
+        f = (rng.random(n) < 0.37).astype(np.uint8)
+        if n > 2000:
+            f[5000:9000] = 1                                  # whole CTAs without survivors
+            f[20000:26000] = 0                                # ... and full ones
+        for keep in (0, 1):
+            idx, cnt = ops.compact_u8(dev(f) if n else torch.zeros([0], dtype=torch.uint8, device="cuda"), keep)
+            want = np.nonzero(f == keep)[0]
+            assert int(cnt.item()) == len(want)
+            assert np.array_equal(idx[:len(want)].cpu().numpy(), want)
