@@ -75,8 +75,8 @@ int ppnet_lvc_f32(const float* wp, const int64_t* path_off, const int32_t* path_
 
 /* ---- A14  MapGenerate.generate_map_randomly clearance verdict  EDaGe-PP/MapGenerate.py:132-143
  *      pathpt[M][np][2] (row, col) float64; cand[M][O][3] = (x, y, r) in map units.
- *      accept[M][O]; out[M][O][3] = accepted [col_px, row_px, r_px] compacted in order;
- *      out_cnt[M].                                                                               */
+ *      accept[M][O]; out[M][O][3] = accepted [col_px, row_px, r_px] compacted in order (rows >= out_cnt[m]
+ *      are left untouched); out_cnt[M].                                                                               */
 int ppnet_clearance_filter_f64(const double* pathpt, int32_t np, const double* cand, int32_t O,
                                int64_t n_maps, double map_size, double resolution, double clearance,
                                uint8_t* accept, double* out, int32_t* out_cnt, void* stream);

@@ -288,3 +288,50 @@ def test_generated_by_planners_mirror_writes_the_reference_files(golden, tmp_pat
         assert os.listdir("data_RRTstar/mask_path") == []                  # Time >= 59 is filtered out
     finally:
         os.chdir(cwd)
+
+
+def test_host_buffer_entry_points_equal_the_device_ops():
+    """Every *_host symbol (pageable numpy in / out, slices on two streams) == the device op it wraps, incl. ragged CSR
+    batches that span several slices."""
+    from ppnet_b200 import host, ops
+    rng = np.random.default_rng(17)
+    ctx = host.HostContext(0)
+    M, omax = 4000, 50
+    obs = np.zeros([M, omax, 3])
+    obs[..., 0] = rng.uniform(0, 224, (M, omax)); obs[..., 1] = rng.uniform(0, 224, (M, omax)); obs[..., 2] = rng.uniform(0, 22, (M, omax))
+    cnt = rng.integers(0, omax + 1, M).astype(np.int32)
+    per = rng.integers(0, 700, M)                               # ~1.4 M segments -> two 2^20-segment slices
+    per[7] = 0
+    off = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+    n = int(off[-1])
+    s = rng.uniform(0, 224, (n, 2))
+    segs = np.concatenate([s, s + rng.normal(0, 15, (n, 2))], axis=1)
+    segs32 = segs.astype(np.float32)
+    d = lambda a: torch.from_numpy(a).cuda()
+    want64 = ops.segcheck_edage_f64(d(segs), d(obs), d(cnt), C, seg_off=d(off)).cpu().numpy()
+    assert np.array_equal(ctx.segcheck_edage_f64(segs, obs, cnt, C, seg_off=off), want64)
+    w32, wst = ops.segcheck_mpnet_f32(d(segs32), d(obs), d(cnt), C, seg_off=d(off), want_steer=True)
+    steer = np.empty(n, dtype=np.uint8)
+    assert np.array_equal(ctx.segcheck_mpnet_f32(segs32, obs, cnt, C, seg_off=off, steer=steer), w32.cpu().numpy())
+    assert np.array_equal(steer, wst.cpu().numpy())
+    bits = ops.raster_circles_bits(d(obs), d(cnt), 224, C / 2)
+    wv, wf = ops.dda_gridcheck(bits, 224, d(segs32), seg_off=d(off))
+    fh = np.empty(n, dtype=np.int32)
+    assert np.array_equal(ctx.dda_gridcheck(bits.cpu().numpy(), 224, segs32, seg_off=off, first_hit=fh), wv.cpu().numpy())
+    assert np.array_equal(fh, wf.cpu().numpy())
+    # uniform grouping, A14, GMM
+    Mu = 5000                                                    # > one 4096-map slice
+    pp = rng.uniform(20, 200, (Mu, 200, 2))
+    cand = np.stack([rng.uniform(0, 50, (Mu, 20)), rng.uniform(0, 50, (Mu, 20)), rng.uniform(0, 5, (Mu, 20))], axis=2)
+    acc, out, oc = ctx.clearance_filter_f64(pp, cand, 50.0, 224.0, 1.0)
+    wa, wo, wc = ops.clearance_filter_f64(d(pp), d(cand), 50.0, 224.0, 1.0)
+    assert np.array_equal(acc, wa.cpu().numpy()) and np.array_equal(oc, wc.cpu().numpy())
+    wo = wo.cpu().numpy()
+    for m in range(0, Mu, 13):                                   # rows >= out_cnt are unspecified
+        assert np.array_equal(out[m, :oc[m]], wo[m, :oc[m]])
+    mean, std, w = ops.gmm_params(3, 10, 2, 70.0, 5.0)
+    got = ctx.gmm_sample(3, 1234, 5_000_000, mean.cpu().numpy(), std.cpu().numpy(), w.cpu().numpy())
+    assert np.array_equal(got, ops.gmm_sample(3, 1234, 5_000_000, mean, std, w).cpu().numpy())
+    h2d, d2h = ctx.bytes_moved()
+    assert h2d > 0 and d2h > 0
+    ctx.close()
