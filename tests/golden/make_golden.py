@@ -680,7 +680,10 @@ def gen_planner_masks():
 
 
 GENS = {
-    "segcheck_f64": lambda: gen_segcheck("f64", "segcheck_f64.npz"),
+    # run a second time under OPENBLAS_CORETYPE=HASWELL (set before numpy loads) to pin the un-fused ddot model:
+    #   OPENBLAS_CORETYPE=HASWELL python make_golden.py --only segcheck_f64   ->  segcheck_f64_unfused.npz
+    "segcheck_f64": lambda: gen_segcheck("f64", "segcheck_f64.npz" if detect_dot_mode() == orc.DOT_FUSED_SKX
+                                         else "segcheck_f64_unfused.npz"),
     "segcheck_f32": lambda: gen_segcheck("f32", "segcheck_f32.npz"),
     "grid": gen_grid,
     "paths": gen_paths,

@@ -38,8 +38,9 @@ def _rc(segs_xy):
 
 
 # ------------------------------------------------------------------ A11
-def test_segcheck_f64_golden(ops, golden):
-    g = golden("segcheck_f64")
+@pytest.mark.parametrize("fixture", ["segcheck_f64", "segcheck_f64_unfused"])
+def test_segcheck_f64_golden(ops, golden, fixture):
+    g = golden(fixture)                                   # reference outputs under the fused / un-fused OpenBLAS ddot
     order, off = _csr(g["seg_map"], len(g["obs_cnt"]))
     pts = _rc(g["segs_xy"])[order]
     v = ops.segcheck_edage_f64(dev(pts), dev(g["obs"]), dev(g["obs_cnt"]), float(g["clearance"]),

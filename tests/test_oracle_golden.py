@@ -13,8 +13,14 @@ def _rc(segs_xy):
     return np.stack([segs_xy[:, 1], segs_xy[:, 0], segs_xy[:, 3], segs_xy[:, 2]], axis=1)
 
 
-def test_segcheck_f64_python_oracle_vs_reference(golden):
-    g = golden("segcheck_f64")
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("fixture", ["segcheck_f64", "segcheck_f64_unfused"])
+def test_segcheck_f64_python_oracle_vs_reference(golden, fixture):
+    """`segcheck_f64` was produced by the reference under OpenBLAS' SkylakeX ddot (fused), `segcheck_f64_unfused` by the
+    same code under OPENBLAS_CORETYPE=HASWELL (un-fused): both ddot models are pinned by real reference outputs."""
+    g = golden(fixture)
     segs, mp, obs, cnt = g["segs_xy"], g["seg_map"], g["obs"], g["obs_cnt"]
     mode = int(g["dot_mode"])
     rc = _rc(segs)
@@ -28,8 +34,10 @@ def test_segcheck_f64_python_oracle_vs_reference(golden):
     assert bad == 0
 
 
-def test_segcheck_f64_c_oracle_vs_reference(golden):
-    g = golden("segcheck_f64")
+@pytest.mark.parametrize("fixture", ["segcheck_f64", "segcheck_f64_unfused"])
+def test_segcheck_f64_c_oracle_vs_reference(golden, fixture):
+    g = golden(fixture)
+    assert int(g["dot_mode"]) == (0 if fixture == "segcheck_f64" else 1)
     v = c_oracle.segcheck_f64(_rc(g["segs_xy"]), g["seg_map"], g["obs"], g["obs_cnt"],
                               float(g["clearance"]), dot_mode=int(g["dot_mode"]), threads=2)
     assert np.array_equal(v, g["verdict"])
