@@ -263,10 +263,10 @@ constexpr int kQueueCap = 512;                   // pairs per round (16 per lane
 constexpr int kTakeMax = kQueueCap / 32;
 
 // resident CTAs per SM the compiler must allow: f64 needs its 80 registers (spills cost more than occupancy gives),
-// f32 is better off at 64 registers and 8 CTAs (measured)
+// f32 is best at 72 registers and 7 CTAs (measured: 5 / 6 / 7 / 8 / 9 / 10 CTAs -> 0.319 / 0.290 / 0.273 / 0.279 / 0.297 / 0.314 ms)
 template <typename T> struct SegOcc;
 template <> struct SegOcc<double> { static constexpr int kMinBlocks = 6; };
-template <> struct SegOcc<float> { static constexpr int kMinBlocks = 8; };
+template <> struct SegOcc<float> { static constexpr int kMinBlocks = 7; };
 
 template <typename T>
 struct __align__(16) SegSlot {                   // what a pair needs of its segment (d, |d|^2 are recomputed)
