@@ -2,6 +2,8 @@
 // A5  Path.free_space_bydirection  EDaGe-PP/Path.py:397-404   -- the float ray-march, and the four
 //     driver loops of Path.path_space :113-134.
 // Both bit-exact: float64 divide, add, round-half-to-even (rint), no contraction.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ppnet {
@@ -29,8 +31,8 @@ __global__ void grid_index_kernel(const double* __restrict__ pts, int64_t n, dou
 // one thread per ray; rays of one corridor paint the same W x H byte image (benign same-value races)
 __global__ void corridor_paint_kernel(const double* __restrict__ x0, const double* __restrict__ dir,
                                       const double* __restrict__ step_num, int rays_per_path, double step,
-                                      double off, int W, int H, uint8_t value, uint8_t* __restrict__ space) {
-    const int64_t p = blockIdx.y;
+                                      double off, int W, int H, uint8_t value, uint8_t* __restrict__ space, int64_t p0) {
+    const int64_t p = p0 + blockIdx.y;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rays_per_path) return;
     const size_t ri = ((size_t)p * rays_per_path + r) * 2;
@@ -53,8 +55,8 @@ __global__ void corridor_paint_kernel(const double* __restrict__ x0, const doubl
 // the two roundings are kept separate:  (i, j) -> (rint(i - ty), rint(j - tx)) -> rotate by d about (Ws-1)/2 -> rint.
 // Identical pixels to the reference on all golden corridors (float64 here, float32 grids there).
 __global__ void mask_rigid_kernel(const uint8_t* __restrict__ src, int Ws, const double* __restrict__ angle_deg,
-                                  const double* __restrict__ translate, int Ro, uint8_t* __restrict__ out) {
-    const int64_t m = blockIdx.y;
+                                  const double* __restrict__ translate, int Ro, uint8_t* __restrict__ out, int64_t m0) {
+    const int64_t m = m0 + blockIdx.y;
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     if (px >= Ro * Ro) return;
     const int i = px / Ro, j = px % Ro;
@@ -82,10 +84,11 @@ extern "C" int ppnet_mask_rigid(const uint8_t* src, int32_t Ws, const double* an
     PPNET_REQUIRE(n >= 0 && Ws > 0 && Ro > 0, "mask_rigid: bad sizes");
     if (n == 0) return PPNET_OK;
     PPNET_REQUIRE(src && angle_deg && translate && out, "mask_rigid: null pointer");
-    PPNET_REQUIRE(n <= 65535, "mask_rigid: at most 65535 masks per launch");
-    dim3 grid((unsigned)((Ro * Ro + 255) / 256), (unsigned)n);
-    mask_rigid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, Ws, angle_deg, translate, Ro, out);
-    PPNET_LAUNCH_CHECK("mask_rigid_kernel");
+    for (int64_t m0 = 0; m0 < n; m0 += 65535) {                 // grid.y limit: launch in chunks of 65535 masks
+        dim3 grid((unsigned)((Ro * Ro + 255) / 256), (unsigned)std::min<int64_t>(65535, n - m0));
+        mask_rigid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, Ws, angle_deg, translate, Ro, out, m0);
+        PPNET_LAUNCH_CHECK("mask_rigid_kernel");
+    }
     return PPNET_OK;
 }
 
@@ -111,11 +114,12 @@ extern "C" int ppnet_corridor_paint(const double* x0, const double* dir, const d
     PPNET_REQUIRE(n_paths >= 0 && rays_per_path >= 0 && W > 0 && H > 0, "corridor_paint: bad sizes");
     if (n_paths == 0 || rays_per_path == 0) return PPNET_OK;
     PPNET_REQUIRE(x0 && dir && step_num && space, "corridor_paint: null pointer");
-    PPNET_REQUIRE(n_paths <= 65535, "corridor_paint: at most 65535 paths per launch");
     const double step = map_size / resolution;
-    dim3 grid((unsigned)((rays_per_path + 127) / 128), (unsigned)n_paths);
-    corridor_paint_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x0, dir, step_num, rays_per_path, step,
-                                                                   mapoffset, W, H, value, space);
-    PPNET_LAUNCH_CHECK("corridor_paint_kernel");
+    for (int64_t p0 = 0; p0 < n_paths; p0 += 65535) {           // grid.y limit: chunks of 65535 corridors
+        dim3 grid((unsigned)((rays_per_path + 127) / 128), (unsigned)std::min<int64_t>(65535, n_paths - p0));
+        corridor_paint_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x0, dir, step_num, rays_per_path, step,
+                                                                       mapoffset, W, H, value, space, p0);
+        PPNET_LAUNCH_CHECK("corridor_paint_kernel");
+    }
     return PPNET_OK;
 }

@@ -14,8 +14,9 @@
 namespace ppnet {
 
 // one thread per (map, sampled point)
-__global__ void path_mask_kernel(const double* __restrict__ pathpt, int np, int stride, int R, uint8_t* __restrict__ out) {
-    const int64_t m = blockIdx.y;
+__global__ void path_mask_kernel(const double* __restrict__ pathpt, int np, int stride, int R, uint8_t* __restrict__ out,
+                                 int64_t m0) {
+    const int64_t m = m0 + blockIdx.y;
     const int k = (blockIdx.x * blockDim.x + threadIdx.x) * stride;        // step % stride == 0
     if (k >= np) return;
     const double* p = pathpt + ((size_t)m * np + k) * 2;
@@ -95,8 +96,8 @@ extract_path_kernel(const float* __restrict__ mask, int h, int w, const double* 
 // steps of 1/224 px (K = round(clearance / 2 * 224) = 502 at the reference's clearance).  Cells are stored in the
 // orientation of the saved files (row = y, col = x).
 __global__ void planner_mask_kernel(const double* __restrict__ wp, const int64_t* __restrict__ path_off, int K, int R,
-                                    int pps, uint8_t* __restrict__ space, uint8_t* __restrict__ pathm) {
-    const int64_t m = blockIdx.y;
+                                    int pps, uint8_t* __restrict__ space, uint8_t* __restrict__ pathm, int64_t m0) {
+    const int64_t m = m0 + blockIdx.y;
     const int64_t lo = path_off[m], L = path_off[m + 1] - lo;
     if (L < 2) return;
     const double2* p = reinterpret_cast<const double2*>(wp) + lo;
@@ -157,15 +158,17 @@ extern "C" int ppnet_planner_masks(const double* wp, const int64_t* path_off, in
     PPNET_REQUIRE(n_paths >= 0 && resolution > 1 && points_per_seg > 0 && max_len >= 0, "planner_masks: bad sizes");
     if (n_paths == 0) return PPNET_OK;
     PPNET_REQUIRE(wp && path_off && mask_space && mask_path, "planner_masks: null pointer");
-    PPNET_REQUIRE(n_paths <= 65535, "planner_masks: at most 65535 solutions per launch");
     const size_t bytes = (size_t)n_paths * resolution * resolution;
     PPNET_CUDA(cudaMemsetAsync(mask_space, 0, bytes, (cudaStream_t)stream));
     PPNET_CUDA(cudaMemsetAsync(mask_path, 0, bytes, (cudaStream_t)stream));
     const int K = (int)nearbyint(clearance / 2.0 / (1.0 / 224.0));                    // round(clearance / 2 / step_img)
     const int64_t rays = 720 + std::max<int64_t>(max_len - 1, 0) * points_per_seg * 2;
-    dim3 grid((unsigned)((rays + 127) / 128), (unsigned)n_paths);
-    planner_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(wp, path_off, K, resolution, points_per_seg, mask_space, mask_path);
-    PPNET_LAUNCH_CHECK("planner_mask_kernel");
+    for (int64_t m0 = 0; m0 < n_paths; m0 += 65535) {           // grid.y limit: chunks of 65535 solutions
+        dim3 grid((unsigned)((rays + 127) / 128), (unsigned)std::min<int64_t>(65535, n_paths - m0));
+        planner_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(wp, path_off, K, resolution, points_per_seg, mask_space,
+                                                                    mask_path, m0);
+        PPNET_LAUNCH_CHECK("planner_mask_kernel");
+    }
     return PPNET_OK;
 }
 
@@ -174,13 +177,14 @@ extern "C" int ppnet_path_mask(const double* pathpt, int32_t np, int64_t n_maps,
     PPNET_REQUIRE(n_maps >= 0 && np >= 0 && stride > 0 && resolution > 0, "path_mask: bad sizes");
     if (n_maps == 0) return PPNET_OK;
     PPNET_REQUIRE(pathpt && out, "path_mask: null pointer");
-    PPNET_REQUIRE(n_maps <= 65535, "path_mask: at most 65535 maps per launch");
     PPNET_CUDA(cudaMemsetAsync(out, 0, (size_t)n_maps * resolution * resolution, (cudaStream_t)stream));
     const int pts = (np + stride - 1) / stride;
     if (pts == 0) return PPNET_OK;
-    dim3 grid((unsigned)((pts + 127) / 128), (unsigned)n_maps);
-    path_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pathpt, np, stride, resolution, out);
-    PPNET_LAUNCH_CHECK("path_mask_kernel");
+    for (int64_t m0 = 0; m0 < n_maps; m0 += 65535) {            // grid.y limit: chunks of 65535 maps
+        dim3 grid((unsigned)((pts + 127) / 128), (unsigned)std::min<int64_t>(65535, n_maps - m0));
+        path_mask_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(pathpt, np, stride, resolution, out, m0);
+        PPNET_LAUNCH_CHECK("path_mask_kernel");
+    }
     return PPNET_OK;
 }
 

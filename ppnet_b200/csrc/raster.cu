@@ -34,8 +34,8 @@ raster_kernel(const double* __restrict__ obs, const int32_t* __restrict__ obs_cn
 // A15's return value + MapGenerate.py:111-113: map image f32[3][R][R], 1 = free (white), 0 = obstacle (black),
 // optionally + the placed corridor mask, then A16's two 7x7 red stamps.
 __global__ void bits_to_image_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restrict__ add,
-                                     float* __restrict__ img) {
-    const int64_t m = blockIdx.y;
+                                     float* __restrict__ img, int64_t m0) {
+    const int64_t m = m0 + blockIdx.y;
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     if (px >= R * R) return;
     const int i = px / R, j = px % R;
@@ -76,11 +76,12 @@ extern "C" int ppnet_bits_to_image(const uint32_t* bits, int32_t resolution, int
     PPNET_REQUIRE(n_maps >= 0 && resolution > 0, "bits_to_image: bad sizes");
     if (n_maps == 0) return PPNET_OK;
     PPNET_REQUIRE(bits && image, "bits_to_image: null pointer");
-    PPNET_REQUIRE(n_maps <= 65535, "bits_to_image: at most 65535 maps per call");
     const int W = (resolution + 31) / 32;
-    dim3 grid((unsigned)((resolution * resolution + 255) / 256), (unsigned)n_maps);
-    bits_to_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, resolution, W, add, image);
-    PPNET_LAUNCH_CHECK("bits_to_image_kernel");
+    for (int64_t m0 = 0; m0 < n_maps; m0 += 65535) {            // grid.y limit: chunks of 65535 maps
+        dim3 grid((unsigned)((resolution * resolution + 255) / 256), (unsigned)(n_maps - m0 < 65535 ? n_maps - m0 : 65535));
+        bits_to_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(bits, resolution, W, add, image, m0);
+        PPNET_LAUNCH_CHECK("bits_to_image_kernel");
+    }
     return PPNET_OK;
 }
 

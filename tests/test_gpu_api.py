@@ -335,3 +335,25 @@ def test_host_buffer_entry_points_equal_the_device_ops():
     h2d, d2h = ctx.bytes_moved()
     assert h2d > 0 and d2h > 0
     ctx.close()
+
+
+def test_per_item_kernels_accept_more_than_65535_items():
+    """Launches whose grid.y is the item index are chunked inside the C ABI."""
+    from ppnet_b200 import ops
+    n = 70001
+    rng = np.random.default_rng(2)
+    pp = rng.uniform(0, 16, (n, 10, 2))
+    m = ops.path_mask(torch.from_numpy(pp).cuda(), resolution=16, stride=5).cpu().numpy()
+    for i in (0, 65534, 65535, 65536, n - 1):
+        assert np.array_equal(m[i], orc.gen_path_mask(pp[i], 16))
+    src = torch.from_numpy((rng.random((n, 8, 8)) < 0.5).astype(np.uint8) * 255).cuda()
+    ang = torch.from_numpy(rng.uniform(-180, 180, n)).cuda()
+    tr = torch.from_numpy(rng.integers(-2, 3, (n, 2)).astype(np.float64)).cuda()
+    out = ops.mask_rigid(src, ang, tr, 8).cpu().numpy()
+    for i in (0, 65535, 65536, n - 1):
+        assert np.array_equal(out[i], orc.mask_rigid(src[i].cpu().numpy(), float(ang[i]), tr[i].cpu().numpy(), 8))
+    bits = torch.from_numpy(rng.integers(0, 2 ** 31, (n, 8, 1)).astype(np.int32)).cuda()
+    img = ops.bits_to_image(bits, 8)
+    assert img.shape == (n, 3, 8, 8) and float(img[n - 1].max()) <= 1.0
+    b_last = int(bits[n - 1, 3, 0].item())
+    assert [float(v) for v in img[n - 1, 0, 3]] == [0.0 if (b_last >> j) & 1 else 1.0 for j in range(8)]
