@@ -352,3 +352,30 @@ def test_compact_survivors(ops):
             want = np.nonzero(f == keep)[0]
             assert int(cnt.item()) == len(want)
             assert np.array_equal(idx[:len(want)].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("flavour", ["f64", "f32"])
+def test_verdict_monotonicity_properties(ops, flavour):
+    """Size-independent properties of the verdict (an OR over circles of two monotone tests): adding a circle or
+    growing radii / clearance can only turn 'free' into 'collision'; removing every circle leaves only the bounds rule."""
+    rng = np.random.default_rng(12)
+    M, spm, omax = 500, 1024, 40
+    ft = np.float64 if flavour == "f64" else np.float32
+    segs, obs, cnt = _config2_inputs(rng, M, spm, ft, omax=omax)
+    cnt = np.minimum(cnt, omax - 1).astype(np.int32)
+    fn = (lambda s, o, c, cl: ops.segcheck_edage_f64(s, o, c, cl)) if flavour == "f64" else \
+         (lambda s, o, c, cl: ops.segcheck_mpnet_f32(s, o, c, cl))
+    S, Ob, Cn = dev(segs), dev(obs), dev(cnt)
+    v = fn(S, Ob, Cn, CLEAR)
+    obs2 = obs.copy()
+    obs2[np.arange(M), cnt] = np.stack([rng.uniform(0, 224, M), rng.uniform(0, 224, M), rng.uniform(0, 22, M)], axis=1)
+    v_more = fn(S, dev(obs2), dev(cnt + 1), CLEAR)
+    assert bool((v_more >= v).all()) and bool((v_more > v).any())
+    obs3 = obs.copy()
+    obs3[..., 2] *= 1.25
+    assert bool((fn(S, dev(obs3), Cn, CLEAR) >= v).all())
+    assert bool((fn(S, Ob, Cn, 2 * CLEAR) >= v).all())
+    v_none = fn(S, Ob, dev(np.zeros(M, dtype=np.int32)), CLEAR).cpu().numpy()
+    a = segs.astype(np.float64)
+    oob = (a[:, 0] < 0) | (a[:, 1] > 224) | (a[:, 2] < 0) | (a[:, 3] > 224)      # same rule on the raw inputs in both flavours
+    assert np.array_equal(v_none.astype(bool), oob)
