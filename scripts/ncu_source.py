@@ -1,8 +1,10 @@
 """Per-source-line hot spots of one kernel from an .ncu-rep (needs -lineinfo + --import-source on):
-   python scripts/ncu_source.py rep kernel-regex [top]"""
+   python scripts/ncu_source.py rep kernel-regex [top] [function-name-substring]"""
 import csv, subprocess, sys
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+only = sys.argv[4] if len(sys.argv) > 4 else None
+keep = True
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
                       "regex:" + pat], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -14,7 +16,12 @@ names = ["# Samples", "Instructions Executed", "Thread Instructions Executed", "
 for r in rows:
     if not r: continue
     if r[0] == "File Path": fname = r[1].split("/")[-1]; continue
-    if r[0] == "Function Name": print("== ", r[1][:120]); continue
+    if r[0] == "Function Name":
+        keep = only is None or only in r[1]
+        if keep: print("== ", r[1][:120])
+        cur = None
+        continue
+    if not keep: continue
     if r[0] == "Line No": idx = {h: k for k, h in enumerate(r) if h not in ("Source",)}; continue
     if idx is None: continue
     if r[0].isdigit():
