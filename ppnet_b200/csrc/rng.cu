@@ -43,12 +43,29 @@ constexpr int kGmmMaxK = 64;
 
 // one thread per sample.  block 0 of the sample's counter: x -> component, (y, z) -> Box-Muller pair
 // for dims 0/1; dims >= 2 take further blocks (4 normals each).
+// Box-Muller on (0,1] x [0,1): u1 = (wa + 1) / 2^32 never 0.  SFU transcendentals (MUFU.LG2 / SQRT / SIN / COS,
+// |error| ~ 2^-21): sampling parity is statistical, and the argument of sin / cos is folded into [-pi, pi) where the
+// hardware approximations are at their best: cos(2 pi u) = -cos(2 pi u - pi), sin(2 pi u) = -sin(2 pi u - pi)
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
+    const float u1 = ((float)(wa >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = u24(wb);
+    float rad;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);
+    z0 = rad * -cs;
+    z1 = rad * -sn;
+}
+
+// kPlanar: D == 2 (the reference's only use, MapGenerate.py / GMM.py): parameters as float2 in shared memory, one
+// 8-byte store per sample, no per-dimension loop.
+template <bool kPlanar>
 __global__ void __launch_bounds__(256)
 gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const float* __restrict__ mean,
                   const float* __restrict__ stdv, const float* __restrict__ w, float* __restrict__ out,
                   int32_t* __restrict__ comp) {
     __shared__ float cdf[kGmmMaxK];
-    __shared__ float s_mean[kGmmMaxK * 4], s_std[kGmmMaxK * 4];
+    __shared__ __align__(8) float s_mean[kGmmMaxK * 4], s_std[kGmmMaxK * 4];
     if (threadIdx.x == 0) {                               // normalised inclusive CDF, serial f32 sum
         float tot = 0.f;
         for (int k = 0; k < K; ++k) tot = __fadd_rn(tot, w[k]);
@@ -60,40 +77,39 @@ gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const fl
     __syncthreads();
     // persistent grid-stride loop: the CDF / parameter staging above is paid once per CTA, not once per 256 samples
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t g = sample0 + (uint64_t)i;
-    uint4 r = Philox::gen(key, make_uint4(0u, STREAM_GMM_SAMPLE, (uint32_t)g, (uint32_t)(g >> 32)));
-    const float uc = u24(r.x);
-    int k = 0;                                            // inverse CDF: the CDF is non-decreasing, so the first k with
-    for (int j = 0; j < K - 1; ++j) k += (uc >= cdf[j]);  // uc < cdf[k] is the count of entries <= uc (branch-free)
-    if (comp) comp[i] = k;
-    uint32_t wa = r.y, wb = r.z;
-    for (int d = 0; d < D; d += 2) {
-        if (d >= 2) {
-            const int q = (d - 2) >> 1;                   // pair index among the extra blocks
-            if ((q & 1) == 0) r = Philox::gen(key, make_uint4(1u + (uint32_t)(q >> 1), STREAM_GMM_SAMPLE,
-                                                             (uint32_t)g, (uint32_t)(g >> 32)));
-            wa = (q & 1) ? r.z : r.x;
-            wb = (q & 1) ? r.w : r.y;
+        const uint64_t g = sample0 + (uint64_t)i;
+        uint4 r = Philox::gen(key, make_uint4(0u, STREAM_GMM_SAMPLE, (uint32_t)g, (uint32_t)(g >> 32)));
+        const float uc = u24(r.x);
+        int k = 0;                                            // inverse CDF: the CDF is non-decreasing, so the first k with
+        for (int j = 0; j < K - 1; ++j) k += (uc >= cdf[j]);  // uc < cdf[k] is the count of entries <= uc (branch-free)
+        if (comp) comp[i] = k;
+        if (kPlanar) {
+            float z0, z1;
+            box_muller(r.y, r.z, z0, z1);
+            const float2 mu = reinterpret_cast<const float2*>(s_mean)[k], sd = reinterpret_cast<const float2*>(s_std)[k];
+            reinterpret_cast<float2*>(out)[i] = make_float2(mu.x + sd.x * z0, mu.y + sd.y * z1);
+            continue;
         }
-        // Box-Muller on (0,1] x [0,1): u1 = (wa + 1) / 2^32 never 0
-        const float u1 = ((float)(wa >> 8) + 1.0f) * (1.0f / 16777216.0f);
-        const float u2 = u24(wb);
-        // SFU transcendentals (MUFU.LG2 / SIN / COS, |error| ~ 2^-21): sampling parity is statistical, and the argument of
-        // sin / cos is folded into [-pi, pi) where the hardware approximations are at their best:
-        // cos(2 pi u) = -cos(2 pi u - pi), sin(2 pi u) = -sin(2 pi u - pi)
-        const float rad = sqrtf(-2.0f * __logf(u1));
-        float sn, cs;
-        __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &sn, &cs);
-        sn = -sn; cs = -cs;
-        const float m0 = cache ? s_mean[k * D + d] : mean[k * D + d];
-        const float s0 = cache ? s_std[k * D + d] : stdv[k * D + d];
-        out[i * D + d] = m0 + s0 * (rad * cs);
-        if (d + 1 < D) {
-            const float m1 = cache ? s_mean[k * D + d + 1] : mean[k * D + d + 1];
-            const float s1 = cache ? s_std[k * D + d + 1] : stdv[k * D + d + 1];
-            out[i * D + d + 1] = m1 + s1 * (rad * sn);
+        uint32_t wa = r.y, wb = r.z;
+        for (int d = 0; d < D; d += 2) {
+            if (d >= 2) {
+                const int q = (d - 2) >> 1;                   // pair index among the extra blocks
+                if ((q & 1) == 0) r = Philox::gen(key, make_uint4(1u + (uint32_t)(q >> 1), STREAM_GMM_SAMPLE,
+                                                                 (uint32_t)g, (uint32_t)(g >> 32)));
+                wa = (q & 1) ? r.z : r.x;
+                wb = (q & 1) ? r.w : r.y;
+            }
+            float z0, z1;
+            box_muller(wa, wb, z0, z1);
+            const float m0 = cache ? s_mean[k * D + d] : mean[k * D + d];
+            const float s0 = cache ? s_std[k * D + d] : stdv[k * D + d];
+            out[i * D + d] = m0 + s0 * z0;
+            if (d + 1 < D) {
+                const float m1 = cache ? s_mean[k * D + d + 1] : mean[k * D + d + 1];
+                const float s1 = cache ? s_std[k * D + d + 1] : stdv[k * D + d + 1];
+                out[i * D + d + 1] = m1 + s1 * z1;
+            }
         }
-    }
     }
 }
 
@@ -135,9 +151,12 @@ extern "C" int ppnet_gmm_sample(uint64_t seed, uint64_t sample0, int64_t n, int3
     if (n == 0) return PPNET_OK;
     PPNET_REQUIRE(mean && stdv && weights && out, "gmm_sample: null pointer");
     const int64_t ctas = std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 8);
-    gmm_sample_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(make_key(seed), sample0, n,
-                                                                                    order, dim, mean, stdv, weights,
-                                                                                    out, comp);
+    if (dim == 2 && (reinterpret_cast<uintptr_t>(out) & 7) == 0)
+        gmm_sample_kernel<true><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(make_key(seed), sample0, n, order, dim, mean,
+                                                                                  stdv, weights, out, comp);
+    else
+        gmm_sample_kernel<false><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(make_key(seed), sample0, n, order, dim, mean,
+                                                                                   stdv, weights, out, comp);
     PPNET_LAUNCH_CHECK("gmm_sample_kernel");
     return PPNET_OK;
 }
