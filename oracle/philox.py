@@ -89,11 +89,12 @@ def gmm_params(seed, order, dim, mean_range, std_range):
 
 
 def gmm_sample(seed, sample0, n, mean, std, w):
-    """dim <= 2 layout: block 0 of sample i: x -> component, (y, z) -> Box-Muller pair (float32 math;
-    the device uses the SFU __logf / __sincosf, so values agree to ~1e-4 absolute, components exactly)."""
+    """Layout (ppnet_b200/csrc/rng.cu): block 0 of sample i: x -> component, (y, z) -> Box-Muller pair of dims 0/1;
+    dims 2q+2, 2q+3 (q >= 0) take block 1 + q // 2, words (x, y) for even q and (z, w) for odd q.  float32 math; the
+    device uses the SFU __logf / __sincosf / sqrt.approx, so values agree to ~1e-4 absolute, components exactly."""
     K, D = mean.shape
-    assert D <= 2
-    r = philox4x32_10(key_of(seed), _ctr(np.zeros(n), STREAM_GMM_SAMPLE, sample0 + np.arange(n, dtype=np.uint64)))
+    idx = sample0 + np.arange(n, dtype=np.uint64)
+    r = philox4x32_10(key_of(seed), _ctr(np.zeros(n), STREAM_GMM_SAMPLE, idx))
     tot = np.float32(0)
     for k in range(K):
         tot = np.float32(tot + w[k])
@@ -103,18 +104,30 @@ def gmm_sample(seed, sample0, n, mean, std, w):
         acc = np.float32(acc + w[k])
         cdf[k] = np.float32(acc / tot)
     uc = u24(r[:, 0])
-    comp = np.minimum((uc[:, None] >= cdf[None, :]).sum(axis=1), K - 1)
+    comp = np.minimum((uc[:, None] >= cdf[None, :K - 1]).sum(axis=1), K - 1) if K > 1 else np.zeros(n, dtype=np.int64)
     # `while k < K-1 and uc >= cdf[k]` stops at the first k with uc < cdf[k]; cdf is non-decreasing
     comp = np.asarray([next((k for k in range(K - 1) if not uc[i] >= cdf[k]), K - 1) for i in range(n)]) if n <= 4096 else comp
-    u1 = ((r[:, 1] >> np.uint32(8)).astype(np.float32) + np.float32(1)) * np.float32(1.0 / 16777216.0)
-    u2 = u24(r[:, 2])
-    rad = np.sqrt(np.float32(-2) * np.log(u1)).astype(np.float32)
-    z0 = rad * np.cos(np.float32(2 * np.pi) * u2).astype(np.float32)
-    z1 = rad * np.sin(np.float32(2 * np.pi) * u2).astype(np.float32)
+
+    def pair(wa, wb):
+        u1 = ((wa >> np.uint32(8)).astype(np.float32) + np.float32(1)) * np.float32(1.0 / 16777216.0)
+        u2 = u24(wb)
+        rad = np.sqrt(np.float32(-2) * np.log(u1)).astype(np.float32)
+        return (rad * np.cos(np.float32(2 * np.pi) * u2).astype(np.float32),
+                rad * np.sin(np.float32(2 * np.pi) * u2).astype(np.float32))
+
     out = np.empty([n, D], dtype=np.float32)
-    out[:, 0] = mean[comp, 0] + std[comp, 0] * z0
-    if D > 1:
-        out[:, 1] = mean[comp, 1] + std[comp, 1] * z1
+    blk = None
+    for d in range(0, D, 2):
+        if d == 0:
+            z0, z1 = pair(r[:, 1], r[:, 2])
+        else:
+            q = (d - 2) >> 1
+            if q % 2 == 0:
+                blk = philox4x32_10(key_of(seed), _ctr(np.full(n, 1 + q // 2), STREAM_GMM_SAMPLE, idx))
+            z0, z1 = pair(blk[:, 2], blk[:, 3]) if q % 2 else pair(blk[:, 0], blk[:, 1])
+        out[:, d] = mean[comp, d] + std[comp, d] * z0
+        if d + 1 < D:
+            out[:, d + 1] = mean[comp, d + 1] + std[comp, d + 1] * z1
     return out, comp.astype(np.int32)
 
 

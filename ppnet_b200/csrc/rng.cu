@@ -71,6 +71,8 @@ gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const fl
         for (int k = 0; k < K; ++k) tot = __fadd_rn(tot, w[k]);
         float acc = 0.f;
         for (int k = 0; k < K; ++k) { acc = __fadd_rn(acc, w[k]); cdf[k] = __fdiv_rn(acc, tot); }
+        // entries the search must never count: the last one (k <= K - 1) and the padding up to 15
+        if (K <= 16) for (int k = K - 1; k < 16; ++k) cdf[k] = 2.0f;
     }
     const bool cache = D <= 4;
     if (cache) for (int i = threadIdx.x; i < K * D; i += blockDim.x) { s_mean[i] = mean[i]; s_std[i] = stdv[i]; }
@@ -80,8 +82,17 @@ gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const fl
         const uint64_t g = sample0 + (uint64_t)i;
         uint4 r = Philox::gen(key, make_uint4(0u, STREAM_GMM_SAMPLE, (uint32_t)g, (uint32_t)(g >> 32)));
         const float uc = u24(r.x);
-        int k = 0;                                            // inverse CDF: the CDF is non-decreasing, so the first k with
-        for (int j = 0; j < K - 1; ++j) k += (uc >= cdf[j]);  // uc < cdf[k] is the count of entries <= uc (branch-free)
+        // inverse CDF: the CDF is non-decreasing (weights >= 0, as torch's Categorical requires), so the first k with
+        // uc < cdf[k] is the count of entries <= uc among the first K - 1: four probes of the padded table, else a scan
+        int k = 0;
+        if (K <= 16) {
+            k += (uc >= cdf[k + 7]) << 3;
+            k += (uc >= cdf[k + 3]) << 2;
+            k += (uc >= cdf[k + 1]) << 1;
+            k += (uc >= cdf[k]);
+        } else {
+            for (int j = 0; j < K - 1; ++j) k += (uc >= cdf[j]);
+        }
         if (comp) comp[i] = k;
         if (kPlanar) {
             float z0, z1;

@@ -148,6 +148,20 @@ def test_gmm_params_and_samples(ops):
         assert ks2.pvalue > 0.01, (d, ks2)
 
 
+@pytest.mark.parametrize("K,D", [(1, 2), (2, 2), (15, 2), (16, 2), (17, 2), (64, 2), (10, 1), (10, 3), (16, 6)])
+def test_gmm_component_pick_and_dims(ops, K, D):
+    """Every order / dimension class of the sampler (planar fast path, padded 16-entry search, long scan, extra Philox
+    blocks for dims >= 2) picks the oracle's components and lands on its values."""
+    mean, std, w = ops.gmm_params(SEED + K, K, D, 70.0, 5.0)
+    m_o, s_o, w_o = ph.gmm_params(SEED + K, K, D, 70.0, 5.0)
+    assert np.array_equal(mean.cpu().numpy(), m_o) and np.array_equal(w.cpu().numpy(), w_o)
+    x, comp = ops.gmm_sample(SEED, 77, 4096, mean, std, w, want_comp=True)
+    xo, co = ph.gmm_sample(SEED, 77, 4096, m_o, s_o, w_o)
+    assert np.array_equal(comp.cpu().numpy(), co)
+    assert len(np.unique(co)) == min(K, len(np.unique(co))) and co.max() <= K - 1
+    np.testing.assert_allclose(x.cpu().numpy(), xo, rtol=2e-4, atol=2e-4)
+
+
 # ------------------------------------------------------------------ raster + DDA
 @pytest.mark.parametrize("R,omax", [(224, 50), (1024, 400), (33, 5)])
 def test_raster_and_dda_vs_oracle(ops, R, omax):
