@@ -254,12 +254,11 @@ void orc_raster_circles_bits(const double* obs, const int32_t* obs_cnt, int omax
             double rr = o[2] + inflate;
             if (!(rr > 0) || !isfinite(rr) || !isfinite(o[0]) || !isfinite(o[1])) continue;
             double r2 = rr * rr;
-            long i0 = (long)floor(o[1] - rr - 1), i1 = (long)ceil(o[1] + rr + 1);
-            long j0 = (long)floor(o[0] - rr - 1), j1 = (long)ceil(o[0] + rr + 1);
-            if (i0 < 0) i0 = 0;
-            if (j0 < 0) j0 = 0;
-            if (i1 > R) i1 = R;
-            if (j1 > R) j1 = R;
+            /* bounding box clamped to the image in double (a cast of +-1e300 to long is undefined) */
+            double fi0 = floor(o[1] - rr - 1), fi1 = ceil(o[1] + rr + 1);
+            double fj0 = floor(o[0] - rr - 1), fj1 = ceil(o[0] + rr + 1);
+            long i0 = fi0 < 0 ? 0 : (fi0 > R ? R : (long)fi0), i1 = fi1 > R ? R : (fi1 < 0 ? 0 : (long)fi1);
+            long j0 = fj0 < 0 ? 0 : (fj0 > R ? R : (long)fj0), j1 = fj1 > R ? R : (fj1 < 0 ? 0 : (long)fj1);
             for (long i = i0; i < i1; ++i) {
                 double dy = ((double)i + 0.5) - o[1];
                 for (long j = j0; j < j1; ++j) {

@@ -30,22 +30,34 @@ __device__ __forceinline__ void disk_rows(int R, double ox, double oy, double rr
     i1 = hi_f > (double)R ? R : (hi_f < 0.0 ? 0 : (int)hi_f);
 }
 
-// One (disk, row) task: the inside set of a row is an interval (every rounded op is monotone in |dx|): guess its
-// ends from sqrt, then settle them with the exact per-pixel rule.
+// One (disk, row) task.  The inside set of a row is an interval (every rounded op is monotone in |dx|); in real
+// arithmetic it is the integers of [a, b], a = ox - h - 0.5, b = ox + h - 0.5, h = sqrt(r2 - dy2), and the rounded rule
+// can only disagree with the real one for a pixel whose |dx| is within ~2 sqrt(2^-53) rr of h.  h comes from the SFU
+// (float sqrt.approx, relative error < 3e-7 with the conversion), so when both a and b are farther than
+// tol = 1e-3 + 1e-5 rr from every integer, [ceil a, floor b] IS the rounded rule's interval (tol/2 exceeds both the
+// error of h and the disagreement band); otherwise (~4 tol of the rows, and every non-finite / clamped case, where the
+// comparisons below are false) the ends are settled pixel by pixel with the exact rule.
 __device__ __forceinline__ void raster_disk_row(uint32_t* bm, int R, int W, double ox, double oy, double rr, int i) {
     const double r2 = __dmul_rn(rr, rr);
     const double dy = __dsub_rn(__dadd_rn((double)i, 0.5), oy);
     const double dy2 = __dmul_rn(dy, dy);
     if (!(dy2 <= r2)) return;                              // even dx = 0 fails
-    const double hw = sqrt(r2 - dy2);
-    double a = ceil(ox - hw - 0.5), b = floor(ox + hw - 0.5);
+    float hwf;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(hwf) : "f"((float)(r2 - dy2)));
+    const double hw = (double)hwf;
+    const double af = ox - hw - 0.5, bf = ox + hw - 0.5;
+    double a = ceil(af), b = floor(bf);
+    const double tol = 1e-3 + 1e-5 * rr, da = a - af, db = bf - b;        // da, db in [0, 1)
+    const bool sure = da > tol && da < 1.0 - tol && db > tol && db < 1.0 - tol && hw < 1e6;
     a = fmin(fmax(a, -2.0), (double)R + 1.0);
     b = fmin(fmax(b, -2.0), (double)R + 1.0);
     int j0 = (int)a, j1 = (int)b;
-    while (j0 > -2 && px_inside(ox, dy2, r2, j0 - 1)) --j0;
-    while (j0 <= j1 && !px_inside(ox, dy2, r2, j0)) ++j0;
-    while (j1 < R + 1 && px_inside(ox, dy2, r2, j1 + 1)) ++j1;
-    while (j1 >= j0 && !px_inside(ox, dy2, r2, j1)) --j1;
+    if (!sure) {
+        while (j0 > -2 && px_inside(ox, dy2, r2, j0 - 1)) --j0;
+        while (j0 <= j1 && !px_inside(ox, dy2, r2, j0)) ++j0;
+        while (j1 < R + 1 && px_inside(ox, dy2, r2, j1 + 1)) ++j1;
+        while (j1 >= j0 && !px_inside(ox, dy2, r2, j1)) --j1;
+    }
     j0 = max(j0, 0);
     j1 = min(j1, R - 1);
     if (j0 <= j1) or_span(bm + i * W, j0, j1);
@@ -54,30 +66,9 @@ __device__ __forceinline__ void raster_disk_row(uint32_t* bm, int R, int W, doub
 // One warp rasterises one disk into bm[R][W] (shared memory): one row span per lane.
 __device__ __forceinline__ void raster_disk_warp(uint32_t* bm, int R, int W, double ox, double oy, double rr) {
     const int lane = threadIdx.x & 31;
-    if (!(rr > 0.0) || !(ox == ox) || !(oy == oy) || isinf(rr) || isinf(ox) || isinf(oy)) return;
-    const double r2 = __dmul_rn(rr, rr);
-    const double lo_f = floor(oy - rr - 1.0), hi_f = ceil(oy + rr + 1.0);
-    const int i0 = lo_f < 0.0 ? 0 : (lo_f > (double)R ? R : (int)lo_f);
-    const int i1 = hi_f > (double)R ? R : (hi_f < 0.0 ? 0 : (int)hi_f);
-    for (int i = i0 + lane; i < i1; i += 32) {
-        const double dy = __dsub_rn(__dadd_rn((double)i, 0.5), oy);
-        const double dy2 = __dmul_rn(dy, dy);
-        if (!(dy2 <= r2)) continue;                        // even dx = 0 fails
-        // the inside set of a row is an interval (every rounded op is monotone in |dx|):
-        // guess its ends from sqrt, then settle them with the exact per-pixel rule.
-        const double hw = sqrt(r2 - dy2);
-        double a = ceil(ox - hw - 0.5), b = floor(ox + hw - 0.5);
-        a = fmin(fmax(a, -2.0), (double)R + 1.0);
-        b = fmin(fmax(b, -2.0), (double)R + 1.0);
-        int j0 = (int)a, j1 = (int)b;
-        while (j0 > -2 && px_inside(ox, dy2, r2, j0 - 1)) --j0;
-        while (j0 <= j1 && !px_inside(ox, dy2, r2, j0)) ++j0;
-        while (j1 < R + 1 && px_inside(ox, dy2, r2, j1 + 1)) ++j1;
-        while (j1 >= j0 && !px_inside(ox, dy2, r2, j1)) --j1;
-        j0 = max(j0, 0);
-        j1 = min(j1, R - 1);
-        if (j0 <= j1) or_span(bm + i * W, j0, j1);
-    }
+    int i0, i1;
+    disk_rows(R, ox, oy, rr, i0, i1);
+    for (int i = i0 + lane; i < i1; i += 32) raster_disk_row(bm, R, W, ox, oy, rr, i);
 }
 
 __device__ __forceinline__ void store_bitmap(const uint32_t* bm, uint32_t* dst, int words) {

@@ -163,6 +163,39 @@ def test_gmm_component_pick_and_dims(ops, K, D):
 
 
 # ------------------------------------------------------------------ raster + DDA
+def test_raster_row_ends_on_the_pixel_lattice(ops):
+    """The row-span shortcut (SFU sqrt + certainty band, raster.cuh) must hand every tie to the exact rule: centres on
+    the half-pixel lattice with Pythagorean / integer / half-integer radii put many pixel centres exactly ON the
+    outline (dx^2 + dy^2 == r^2), others 1 ulp and 1e-4 px off it; huge, tiny and off-screen disks ride along."""
+    R, M, omax = 224, 16, 64
+    rng = np.random.default_rng(11)
+    radii = np.asarray([1.0, 2.0, 2.5, 5.0, 6.5, 10.0, 13.0, 12.5, 25.0, 0.5, 1.5, np.sqrt(2.0) / 2, np.sqrt(50.0), 65.0])
+    obs = np.zeros([M, omax, 3])
+    obs[..., 0] = rng.integers(-20, 2 * R + 40, (M, omax)) * 0.5
+    obs[..., 1] = rng.integers(-20, 2 * R + 40, (M, omax)) * 0.5
+    obs[..., 2] = radii[rng.integers(0, len(radii), (M, omax))]
+    obs[1::4, :, 2] = np.nextafter(obs[1::4, :, 2], 0)                  # 1 ulp inside the tie
+    obs[2::4, :, 2] = np.nextafter(obs[2::4, :, 2], 1e9)                # 1 ulp outside
+    obs[3::4, :, 2] += rng.uniform(-2e-3, 2e-3, obs[3::4, :, 2].shape)  # inside the certainty band, either side
+    obs[0, 0] = [112.0, 112.0, 1e7]
+    obs[0, 1] = [1e15, 5.0, 1e15]
+    obs[0, 2] = [-1e6, 50.5, 1e6 + 30.0]
+    obs[0, 3] = [50.5, 50.5, 1e-300]
+    obs[0, 4] = [50.5, 50.5, 1e300]
+    obs[4, 0] = [1e9, 1e9, 5.0]
+    cnt = np.full(M, omax, np.int32)
+    for inflate in (0.0, 0.5, 2.24):
+        got = ops.raster_circles_bits(dev(obs[1:]), dev(cnt[1:]), R, inflate).cpu().numpy().view(np.uint32)
+        want = c_oracle.raster_circles_bits(obs[1:], cnt[1:], R, inflate, threads=4)
+        assert np.array_equal(got, want), inflate
+    got = ops.raster_circles_bits(dev(obs[:1, 5:]), dev(cnt[:1] - 5), R, 0.0).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, c_oracle.raster_circles_bits(obs[:1, 5:], cnt[:1] - 5, R, 0.0, threads=1))
+    for k in range(5):                                                    # the extreme disks one at a time
+        o1 = np.ascontiguousarray(obs[:1, k:k + 1])
+        got = ops.raster_circles_bits(dev(o1), dev(np.ones(1, np.int32)), R, 0.0).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, c_oracle.raster_circles_bits(o1, np.ones(1, np.int32), R, 0.0, threads=1)), k
+
+
 @pytest.mark.parametrize("R,omax", [(224, 50), (1024, 400), (33, 5)])
 def test_raster_and_dda_vs_oracle(ops, R, omax):
     rng = np.random.default_rng(R)
