@@ -14,8 +14,8 @@
 //   3. candidate circles: drawn (Philox, one thread per candidate) by warps 1.. while warp 0 is busy with step 1.
 //      The staged odd points are grouped into boxes of 16
 //      consecutive points; the (candidate, box) pairs are spread over the CTA (warp = candidate, lane = box,
-//      no cross-lane reduction): a pair is skipped when the
-//      candidate is farther from the box than the threshold plus a 1e7-ulp margin (those points cannot be the
+//      no cross-lane reduction): a pair is skipped when an f32 test on the outward-rounded box puts the
+//      candidate farther from it than the threshold plus a 1e-5 (R + |centre|) margin (those points cannot be the
 //      ones that decide `min(dis) > r_px + c*R/M`), otherwise its points are evaluated with the reference's exact
 //      un-fused arithmetic and folded into the candidate's minimum by a shared-memory atomicMin on the bit
 //      pattern.  One sqrt per candidate; ordered compaction by ballot scan.
@@ -123,6 +123,7 @@ generate_kernel(ppnet_gen_params P) {
     double2* odd = reinterpret_cast<double2*>(smem_raw);
     double2* hull = odd + n_odd;
     double4* box = reinterpret_cast<double4*>(hull + P.hmax + (P.hmax & 1));    // (row_lo, row_hi, col_lo, col_hi), 32-B aligned
+    float4* boxf = reinterpret_cast<float4*>(box);                             // the boxes as stored: f32, rounded outward
     uint32_t* bm = reinterpret_cast<uint32_t*>(box + n_blk);
     double* sobs = reinterpret_cast<double*>(bm + ((words + 3) & ~3));
     double* thr_s = sobs + 3 * omax_out;                                       // [O] r_px + c_px
@@ -164,10 +165,11 @@ generate_kernel(ppnet_gen_params P) {
             const double rimg = __dmul_rn(__ddiv_rn(r, M), R);
             o[0] = q1; o[1] = q0; o[2] = rimg;
             const double thr = __dadd_rn(rimg, thr_c);
-            // squared cull radius: (thr + margin)^2 with the margin ~1e7 ulp of the coordinates involved
-            const double cr = thr + 1e-9 * (R + fabs(q0) + fabs(q1) + fabs(thr));
+            // squared cull radius for the f32 box test: (thr + margin)^2, the margin ~100x the float rounding of the
+            // coordinates involved (boxes are rounded outward, so only the centre's and the subtractions' rounding count)
+            const double cr = thr + 1e-5 * (R + fabs(q0) + fabs(q1) + fabs(thr));
             thr_s[k] = thr;
-            cull_s[k] = cr * cr * (1.0 + 1e-12);
+            cull_s[k] = cr * cr * (1.0 + 1e-5);
             m2_s[k] = 0x7ff0000000000000ull;               // +inf
         }
     }
@@ -263,17 +265,18 @@ generate_kernel(ppnet_gen_params P) {
             const double2 p = odd[i];
             bb.x = fmin(bb.x, p.x); bb.y = fmax(bb.y, p.x); bb.z = fmin(bb.z, p.y); bb.w = fmax(bb.w, p.y);
         }
-        box[b] = bb;
+        boxf[b] = make_float4(__double2float_rd(bb.x), __double2float_ru(bb.y), __double2float_rd(bb.z), __double2float_ru(bb.w));
     }
     __syncthreads();
     // (candidate, box) pairs over the whole CTA: a pair whose box is farther than the cull radius cannot hold
     // the point that decides `min(dis) > r_px + c_px`; the others evaluate their 16 points with the reference's
     // un-fused arithmetic and fold into the candidate's minimum with one shared-memory atomicMin.
     for (int k = warp; k < O; k += kGenWarps) {            // warp <-> candidate, lane <-> box: no index arithmetic
-        const double q1 = sobs[3 * k], q0 = sobs[3 * k + 1], cull2 = cull_s[k];
+        const double q1 = sobs[3 * k], q0 = sobs[3 * k + 1];
+        const float q0f = (float)q0, q1f = (float)q1, cull2 = __double2float_ru(cull_s[k]);
         for (int b = lane; b < n_blk; b += 32) {
-            const double4 bb = box[b];
-            const double ex = fmax(fmax(bb.x - q0, q0 - bb.y), 0.0), ey = fmax(fmax(bb.z - q1, q1 - bb.w), 0.0);
+            const float4 bb = boxf[b];
+            const float ex = fmaxf(fmaxf(bb.x - q0f, q0f - bb.y), 0.0f), ey = fmaxf(fmaxf(bb.z - q1f, q1f - bb.w), 0.0f);
             if (ex * ex + ey * ey > cull2) continue;       // NaN never culls
             double m2 = CUDART_INF;
             const int e = min(n_odd, (b + 1) * kBlkPts);
