@@ -46,12 +46,11 @@ __device__ __forceinline__ void raster_disk_row(uint32_t* bm, int R, int W, doub
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(hwf) : "f"((float)(r2 - dy2)));
     const double hw = (double)hwf;
     const double af = ox - hw - 0.5, bf = ox + hw - 0.5;
-    double a = ceil(af), b = floor(bf);
+    const double a = ceil(af), b = floor(bf);
     const double tol = 1e-3 + 1e-5 * rr, da = a - af, db = bf - b;        // da, db in [0, 1)
     const bool sure = da > tol && da < 1.0 - tol && db > tol && db < 1.0 - tol && hw < 1e6;
-    a = fmin(fmax(a, -2.0), (double)R + 1.0);
-    b = fmin(fmax(b, -2.0), (double)R + 1.0);
-    int j0 = (int)a, j1 = (int)b;
+    // clamp to [-2, R + 1] on the integer side: the conversion saturates (+-inf) and maps NaN to 0 (then `sure` is false)
+    int j0 = max(-2, min(R + 1, __double2int_rz(a))), j1 = max(-2, min(R + 1, __double2int_rz(b)));
     if (!sure) {
         while (j0 > -2 && px_inside(ox, dy2, r2, j0 - 1)) --j0;
         while (j0 <= j1 && !px_inside(ox, dy2, r2, j0)) ++j0;
