@@ -35,11 +35,15 @@ extern "C" {
 #define PPNET_DOT_FUSED_SKX 0  /* np.dot == fma(a1,b1, a0*b0): OpenBLAS SkylakeX ddot (AVX-512 hosts) */
 #define PPNET_DOT_UNFUSED 1    /* np.dot == a0*b0 + a1*b1:     OpenBLAS Haswell/Zen ddot */
 
+#define PPNET_CMP_F32_NEP50 0   /* A12 compares its float32 offsets with float32(thr): NumPy >= 2 (NEP 50)        */
+#define PPNET_CMP_F64_NUMPY1 1  /* ... promoted to float64 against the Python-float thr: NumPy 1.x (torch 1.11 era) */
+
 const char* ppnet_last_error(void);
 int ppnet_version(void);
 /* number of kernel launches this library has enqueued since load (bench.py's gpu_launches) */
 int64_t ppnet_launch_count(void);
-/* sizeof the parameter structs as compiled (0: ppnet_gen_params, 1: ppnet_path_params): layout guard for bindings */
+/* sizeof the parameter structs as compiled (0: ppnet_gen_params, 1: ppnet_path_params, 2: ppnet_pipeline_io): layout
+ * guard for bindings */
 int64_t ppnet_sizeof_params(int32_t which);
 
 /* ---- A11  process_map.collision_check_circle_edge(s, e, obs, clearance)
@@ -57,6 +61,16 @@ int ppnet_segcheck_mpnet_f32(const float* pts_xy, int64_t n_segs, const int64_t*
                              int64_t segs_per_map, int64_t n_maps, const double* obs,
                              const int32_t* obs_cnt, int32_t omax, double clearance, double bound,
                              uint8_t* verdict, uint8_t* steer, void* stream);
+
+/* ---- A11 + A12 fused on ONE read of the segments (the hot path's verdict step).  pts_rc as for A11; the A12 flavour
+ *      runs on (x, y) = (float32(col), float32(row)) of the same segment -- the cast + swap a float32 caller holds.
+ *      Any of the four outputs may be NULL: verdict_* are bytes, vbits_* are bit-packed (bit i & 31 of word i >> 5 =
+ *      segment i; ceil(n_segs / 32) words).  Each flavour is bit-identical to its own entry point above.
+ *      cmp_mode selects the NumPy generation of the A12 threshold comparison (neuralplanner.py:54,66).            */
+int ppnet_verdict_fused(const double* pts_rc, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map,
+                        int64_t n_maps, const double* obs, const int32_t* obs_cnt, int32_t omax, double clearance,
+                        double bound, int32_t dot_mode, int32_t cmp_mode, uint8_t* verdict_f64, uint8_t* verdict_f32,
+                        uint32_t* vbits_f64, uint32_t* vbits_f32, void* stream);
 
 /* ---- A12  feasibility_check(path, idx)  neuralplanner.py:96-102
  *      waypoints wp[total][2] f32, path p owns [path_off[p], path_off[p+1]), uses obstacle set
@@ -154,6 +168,13 @@ int ppnet_add_init_end(float* image, int32_t resolution, const double* init, con
 int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int64_t n_maps,
                         const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
                         int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit, void* stream);
+
+/* the same walk on the A11 array read directly: segs_rc[N][4] = (s_row, s_col, e_row, e_col) float64, walked as
+ * (x, y) = (float32(col), float32(row)) -- identical verdicts to ppnet_dda_gridcheck on that cast + swap.
+ * verdict (bytes) and vbits (bit-packed, ceil(n_segs / 32) words) may each be NULL, not both.                     */
+int ppnet_dda_gridcheck_rc64(const uint32_t* bits, int32_t resolution, int64_t n_maps, const double* segs_rc,
+                             int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, uint8_t* verdict,
+                             int32_t* first_hit, uint32_t* vbits, void* stream);
 
 /* ---- A10 + A13 + A14 (+ A15): the fused map generator, one launch for n_maps maps.
  *      MapGenerate.generate inner block EDaGe-PP/MapGenerate.py:58-124 and generate_map_randomly
@@ -293,6 +314,22 @@ int64_t ppnet_compact_workspace_elems(int64_t n);
 int ppnet_compact_u8(const uint8_t* flags, int64_t n, uint8_t keep, int64_t* out_idx, int64_t* out_count,
                      int64_t* workspace, void* stream);
 
+/* the same for bit-packed verdicts: survivors = segments whose bit is CLEAR in every given array (b, c may be NULL),
+ * e.g. free under A11 and A12 and the DDA.  out_idx int32[n] (first *out_count valid, ascending).                  */
+int64_t ppnet_compact_bits_workspace_elems(int64_t n);
+int ppnet_compact_bits(const uint32_t* a, const uint32_t* b, const uint32_t* c, int64_t n, int32_t idx_base,
+                       int32_t* out_idx, int64_t* out_count, int64_t* workspace, void* stream);
+/* short flag arrays (per-map flags, e.g. the valid paths of a slice): one CTA, out_idx int32 = idx_base + i.      */
+int ppnet_compact_u8_i32(const uint8_t* flags, int64_t n, uint8_t keep, int32_t idx_base, int32_t* out_idx,
+                         int64_t* out_count, void* stream);
+
+/* ---- device-side segment source (north star: "segment proposal"): the config-2 candidate segments of maps
+ *      [map0, map0 + n_maps), s ~ U(0, R)^2, e = s + N(0, sigma^2) per axis, as segs_rc f64[n_maps * segs_per_map][4].
+ *      Segment k of global map g is a pure function of (seed, g, k) (Philox4x32-10), so any sharding gives the same
+ *      bytes and generator-mode callers upload nothing.                                                          */
+int ppnet_propose_segments(uint64_t seed, uint64_t map0, int64_t n_maps, int64_t segs_per_map, double resolution,
+                           double sigma, double* segs_rc, void* stream);
+
 /* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
 int ppnet_ctx_create(int32_t device, void** ctx);
 int ppnet_ctx_destroy(void* ctx);
@@ -324,13 +361,32 @@ int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* para
  * slices overlap.  NULL verdict pointers skip that check.                                                        */
 typedef struct ppnet_pipeline_io {
     const double* segs_rc_f64;     /* [n_maps * segs_per_map][4] (s_row, s_col, e_row, e_col), for verdict_f64  */
-    const float* segs_xy_f32;      /* [n_maps * segs_per_map][4] (s_x, s_y, e_x, e_y), for verdict_f32 / _dda   */
+    const float* segs_xy_f32;      /* [n_maps * segs_per_map][4] (s_x, s_y, e_x, e_y), for verdict_f32 / _dda;
+                                      NULL (with segs_rc_f64 or a device proposal): the float32 flavours run on the
+                                      device-side cast + swap (x, y) = (float32(col), float32(row)) -- ONE upload   */
     int64_t segs_per_map;
     double clearance_px, bound;
-    int32_t dot_mode, reserved;
-    uint8_t* verdict_f64;          /* A11 */
+    int32_t dot_mode, cmp_mode;    /* PPNET_DOT_*, PPNET_CMP_* */
+    uint8_t* verdict_f64;          /* A11, one byte per segment */
     uint8_t* verdict_f32;          /* A12 */
     uint8_t* verdict_dda;          /* integer DDA vs the bit-packed map */
+    /* ---- round 2 (appended; zero-initialise the struct to get the round-1 behaviour) ----
+     * bit-packed verdicts: bit (i & 31) of word (i >> 5) = segment i of this call; ceil(n/32) words each; they need
+     * the one-array mode (segs_xy_f32 == NULL). */
+    uint32_t* vbits_f64;
+    uint32_t* vbits_f32;
+    uint32_t* vbits_dda;
+    /* survivors, compacted on the device with warp scans: ascending segment indices (of this call) that are free
+     * under EVERY verdict requested above, and ascending map indices (relative to map0) with a valid placement */
+    int32_t* free_idx;             /* [n_maps * segs_per_map] capacity */
+    int64_t* free_count;           /* [1] */
+    int32_t* valid_idx;            /* [n_maps] capacity */
+    int64_t* valid_count;          /* [1] */
+    /* device-side segment source: when segs_rc_f64 == NULL and propose_sigma > 0 the candidate segments are drawn on
+     * the device (ppnet_propose_segments with params->seed, the global map index and the resolution): nothing is
+     * uploaded.  out_segs_rc (may be NULL) receives them. */
+    double propose_sigma;
+    double* out_segs_rc;           /* [n_maps * segs_per_map][4] */
 } ppnet_pipeline_io;
 int ppnet_generate_and_check_host(void* ctx, void* bank, const ppnet_gen_params* params, const ppnet_pipeline_io* io);
 int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t resolution, int64_t n_maps,

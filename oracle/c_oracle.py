@@ -84,6 +84,24 @@ def segcheck_f32(pts_xy, seg_map, obs, obs_cnt, clearance, bound=224.0, threads=
     return (out, steer) if want_steer else out
 
 
+def segcheck_f32_cmp(pts_xy, seg_map, obs, obs_cnt, clearance, cmp64, bound=224.0, threads=1):
+    """A12 verdicts with the threshold comparison of either NumPy generation (cmp64 = 1: NumPy 1.x promotes the
+    float32 offset to float64; 0: NEP 50, float32 compare)."""
+    pts = _c(pts_xy, np.float32).reshape(-1, 4)
+    sm, ob, oc = _c(seg_map, np.int32), _c(obs, np.float64), _c(obs_cnt, np.int32)
+    n, omax = len(pts), ob.shape[1]
+    out = np.empty(n, dtype=np.uint8)
+    L = lib()
+
+    def run(lo, hi):
+        L.orc_segcheck_f32_cmp(_p(pts[lo:hi]), _p(sm[lo:hi]), _p(ob), _p(oc), ctypes.c_int(omax),
+                               ctypes.c_double(clearance), ctypes.c_double(bound), ctypes.c_int(int(cmp64)),
+                               ctypes.c_long(hi - lo), _p(out[lo:hi]))
+
+    _fan(n, threads, run)
+    return out
+
+
 def feasible(wp, path_off, path_map, obs, obs_cnt, clearance, bound=224.0, threads=1):
     wp = _c(wp, np.float32).reshape(-1, 2)
     po, pm = _c(path_off, np.int64), _c(path_map, np.int32)

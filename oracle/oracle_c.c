@@ -64,8 +64,10 @@ void orc_segcheck_f64(const double* pts_rc, const int32_t* seg_map, const double
 }
 
 /* ---- A12 experiments/MPNet/neuralplanner.py:43-69, all float32 --------------------------- */
-static int segcheck_f32_one(const float* p, const double* obs, int cnt, double clearance,
-                            double bound) {
+/* cmp64 = 0: NumPy >= 2 (NEP 50): the float32 offsets are compared with float32(size + clearance/2);
+ * cmp64 = 1: NumPy 1.x (the reference's requirements.txt era): np.float32 < Python float promotes to float64. */
+static int segcheck_f32_cmp(const float* p, const double* obs, int cnt, double clearance,
+                            double bound, int cmp64) {
     float s0 = p[0], s1 = p[1], e0 = p[2], e1 = p[3];
     float fb = (float)bound;        /* NEP 50: python scalar compares in f32 (0 and 224 exact) */
     if (s0 < 0.0f || s1 > fb) return 1;
@@ -75,9 +77,11 @@ static int segcheck_f32_one(const float* p, const double* obs, int cnt, double c
     float n0 = d1 / L, n1 = (-d0) / L;
     for (int k = 0; k < cnt; ++k) {
         float o0 = (float)obs[3 * k], o1 = (float)obs[3 * k + 1];
-        float thr = (float)(obs[3 * k + 2] + clearance / 2);    /* f64 sum, one rounding to f32 */
+        double thr64 = obs[3 * k + 2] + clearance / 2;
+        float thr = (float)thr64;                               /* f64 sum, one rounding to f32 */
         float v0 = e0 - o0, v1 = e1 - o1;
-        if (sqrtf(v0 * v0 + v1 * v1) < thr) return 1;
+        float dv = sqrtf(v0 * v0 + v1 * v1);
+        if (cmp64 ? ((double)dv < thr64) : (dv < thr)) return 1;
         float q0 = o0 - s0, q1 = o1 - s1;
         float dis = n0 * q0 + n1 * q1;
         if (dis > 0.0f) { n0 = -n0; n1 = -n1; }
@@ -89,9 +93,12 @@ static int segcheck_f32_one(const float* p, const double* obs, int cnt, double c
         float w0 = p0 - e0, w1 = p1 - e1;
         float nw = sqrtf(w0 * w0 + w1 * w1);
         w0 = w0 / nw; w1 = w1 / nw;
-        if (a < thr && (u0 * w0 + u1 * w1) < 0.0f) return 1;
+        if ((cmp64 ? ((double)a < thr64) : (a < thr)) && (u0 * w0 + u1 * w1) < 0.0f) return 1;
     }
     return 0;
+}
+static int segcheck_f32_one(const float* p, const double* obs, int cnt, double clearance, double bound) {
+    return segcheck_f32_cmp(p, obs, cnt, clearance, bound, 0);
 }
 
 static int steer_one(const float* a, const float* b, const double* obs, int cnt, double clearance,
@@ -115,6 +122,16 @@ void orc_segcheck_f32(const float* pts_xy, const int32_t* seg_map, const double*
         verdict[i] = (uint8_t)segcheck_f32_one(pts_xy + 4 * i, ob, obs_cnt[m], clearance, bound);
         if (steer) steer[i] = (uint8_t)steer_one(pts_xy + 4 * i, pts_xy + 4 * i + 2, ob, obs_cnt[m],
                                                  clearance, bound);
+    }
+}
+
+void orc_segcheck_f32_cmp(const float* pts_xy, const int32_t* seg_map, const double* obs,
+                          const int32_t* obs_cnt, int omax, double clearance, double bound, int cmp64,
+                          long n, uint8_t* verdict) {
+    for (long i = 0; i < n; ++i) {
+        int m = seg_map[i];
+        verdict[i] = (uint8_t)segcheck_f32_cmp(pts_xy + 4 * i, obs + (size_t)m * omax * 3, obs_cnt[m],
+                                               clearance, bound, cmp64);
     }
 }
 

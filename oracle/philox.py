@@ -153,3 +153,22 @@ def path_obst_draws(seed, g, n):
     nb = (n + 3) // 4
     r = philox4x32_10(key_of(seed), _ctr(np.arange(nb), STREAM_PATH_OBST, g))
     return u24(r.reshape(-1))[:n]
+
+
+STREAM_SEGS = 8
+
+
+def propose_segments(seed, g, segs_per_map, resolution, sigma):
+    """Candidate segments of global map g (ppnet_b200/csrc/rng.cu propose_segments_kernel): segment k: block 2k ->
+    start (s_row, s_col) = u53 * R; block 2k+1 -> Box-Muller offset in float64, u1 = u53 + 2^-53 in (0, 1].
+    -> f64[spm, 4] (s_row, s_col, e_row, e_col).  The starts are bit-exact; the ends go through log / sincospi, which
+    differ from libm in the last ulp (tests compare them to ~1e-12 relative)."""
+    k = np.arange(segs_per_map)
+    a = philox4x32_10(key_of(seed), _ctr(2 * k, STREAM_SEGS, g))
+    b = philox4x32_10(key_of(seed), _ctr(2 * k + 1, STREAM_SEGS, g))
+    R = np.float64(resolution)
+    s0, s1 = u53(a[:, 0], a[:, 1]) * R, u53(a[:, 2], a[:, 3]) * R
+    u1 = u53(b[:, 0], b[:, 1]) + 1.0 / 9007199254740992.0
+    rad = np.sqrt(-2.0 * np.log(u1)) * np.float64(sigma)
+    ang = 2.0 * u53(b[:, 2], b[:, 3])
+    return np.stack([s0, s1, s0 + rad * np.cos(np.pi * ang), s1 + rad * np.sin(np.pi * ang)], axis=1)

@@ -157,8 +157,11 @@ def segcheck_edage_f64(s_rc, e_rc, obs, clearance, dot_mode=DOT_FUSED_SKX, bound
 MPNET_CLEARANCE = 1 / 50 * 224      # neuralplanner.py:18
 
 
-def segcheck_mpnet_f32(s, e, obs, clearance=MPNET_CLEARANCE, bound=224.0):
-    """s, e: (x, y) float32 pairs (no swap); obs: iterable of [x, y, r] Python floats."""
+def segcheck_mpnet_f32(s, e, obs, clearance=MPNET_CLEARANCE, bound=224.0, cmp_mode=0):
+    """s, e: (x, y) float32 pairs (no swap); obs: iterable of [x, y, r] Python floats.
+    cmp_mode 0: NumPy >= 2 (NEP 50) -- the np.float32 offsets are compared with float32(size + clearance/2), what this
+    container runs and the goldens record; cmp_mode 1: NumPy 1.x (the reference's requirements.txt era) -- a np.float32
+    scalar against a Python float promotes to float64."""
     s0, s1 = f32(s[0]), f32(s[1])
     e0, e1 = f32(e[0]), f32(e[1])
     if s0 < 0 or s1 > bound:                                    # :44-47
@@ -172,9 +175,11 @@ def segcheck_mpnet_f32(s, e, obs, clearance=MPNET_CLEARANCE, bound=224.0):
         for ox, oy, size in obs:
             o0, o1 = f32(ox), f32(oy)                           # :53
             # Python-float threshold, cast to f32 for the compare (NumPy 2 / NEP 50) :54,66
-            thr = f32(float(size) + float(clearance) / 2)
+            thr64 = float(size) + float(clearance) / 2
+            thr = f32(thr64)
+            lt = (lambda x: float(x) < thr64) if cmp_mode else (lambda x: x < thr)
             v0, v1 = f32(e0 - o0), f32(e1 - o1)
-            if np.sqrt(f32(f32(v0 * v0) + f32(v1 * v1))) < thr:   # :54
+            if lt(np.sqrt(f32(f32(v0 * v0) + f32(v1 * v1)))):   # :54
                 return True
             q0, q1 = f32(o0 - s0), f32(o1 - s1)
             dis = f32(f32(n0 * q0) + f32(n1 * q1))              # np.dot f32, un-fused :57
@@ -188,7 +193,7 @@ def segcheck_mpnet_f32(s, e, obs, clearance=MPNET_CLEARANCE, bound=224.0):
             w0, w1 = f32(p0 - e0), f32(p1 - e1)                 # :64
             nw = np.sqrt(f32(f32(w0 * w0) + f32(w1 * w1)))      # :65
             w0, w1 = f32(w0 / nw), f32(w1 / nw)
-            if a < thr and f32(f32(u0 * w0) + f32(u1 * w1)) < 0:    # :66
+            if lt(a) and f32(f32(u0 * w0) + f32(u1 * w1)) < 0:      # :66
                 return True
     return False
 

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libppnet_b200.so")
+# PPNET_B200_LIB: development override (A/B builds of the same library); the product always loads the in-tree file
+LIB_PATH = os.environ.get("PPNET_B200_LIB") or os.path.join(_HERE, "lib", "libppnet_b200.so")
 _lib = None
 
 

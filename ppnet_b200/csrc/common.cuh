@@ -116,6 +116,7 @@ enum : uint32_t {
     STREAM_UNIFORM = 5,    // ppnet_uniform_f64
     STREAM_PATH = 6,       // path synthesis draws (A1)
     STREAM_PATH_OBST = 7,  // set_obstacles draws (A9)
+    STREAM_SEGS = 8,       // candidate segment proposals of map g (ppnet_propose_segments)
 };
 
 }  // namespace ppnet

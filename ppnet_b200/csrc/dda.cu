@@ -51,10 +51,24 @@ __device__ __noinline__ int walk_slow(const uint32_t* __restrict__ bm, int R, in
     return -1;
 }
 
+// segment sources: float32 (s_x, s_y, e_x, e_y) as the entry point has always taken them, or the A11 array
+// (s_row, s_col, e_row, e_col) float64 read directly -- the same cast + swap the fused verdict kernel applies, so the
+// float32 copy of the segments never has to exist (host pipeline: one upload, three verdicts).
+__device__ __forceinline__ float4 load_seg(const float* segs, int64_t i) {
+    return __ldg(reinterpret_cast<const float4*>(segs) + i);
+}
+__device__ __forceinline__ float4 load_seg(const double* segs, int64_t i) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(segs) + 2 * i);
+    const double2 b = __ldg(reinterpret_cast<const double2*>(segs) + 2 * i + 1);
+    return make_float4((float)a.y, (float)a.x, (float)b.y, (float)b.x);
+}
+
+template <typename TS>
 __global__ void __launch_bounds__(kDdaThreads)
-dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restrict__ segs,
+dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict__ segs,
            const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
-           uint8_t* __restrict__ verdict, int32_t* __restrict__ first_hit) {
+           uint8_t* __restrict__ verdict, int32_t* __restrict__ first_hit, uint32_t* __restrict__ vbits,
+           int exclusive_words) {
     extern __shared__ __align__(128) unsigned char dsm[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);                      // 16 B header: mbarrier, claim counter, parked count
     int* next = reinterpret_cast<int*>(dsm + 8);
@@ -99,7 +113,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
 #pragma unroll
         for (int j = 0; j < kDdaPerThread; ++j) {                          // all loads in flight before the first use
             const int t = threadIdx.x + j * kDdaThreads;
-            sv[j] = t < ns ? __ldg(reinterpret_cast<const float4*>(segs) + st0 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sv[j] = t < ns ? load_seg(segs, st0 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (threadIdx.x == 0) { *next = 0; *parked = 0; }
         __syncthreads();                                                   // orders the barrier init / plain bitmap loads / counters
@@ -218,10 +232,25 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
         }
         __syncthreads();
         // ---- 3. flush the stage's results (coalesced) ----------------------------------------------------------
-        for (int t = threadIdx.x; t < ns; t += kDdaThreads) {
-            const int rr = res[t];
-            verdict[st0 + t] = (uint8_t)(rr >= 0);
-            if (first_hit) first_hit[st0 + t] = rr;
+        for (int t0 = 0; t0 < ns; t0 += kDdaThreads) {                   // uniform trip count: the ballot below is warp-wide
+            const int t = t0 + threadIdx.x;
+            const int rr = t < ns ? res[t] : -1;
+            if (t < ns) {
+                if (verdict) verdict[st0 + t] = (uint8_t)(rr >= 0);
+                if (first_hit) first_hit[st0 + t] = rr;
+            }
+            if (vbits) {                                                   // bit (i & 31) of word (i >> 5) = segment i
+                const uint32_t m = __ballot_sync(0xffffffffu, rr >= 0);
+                if (lane == 0 && t < ns) {
+                    const int64_t i0 = st0 + t, k = i0 >> 5;
+                    const int sh = (int)(i0 & 31);
+                    if (exclusive_words) vbits[k] = m;
+                    else {                                                 // shared words were zeroed by the launcher
+                        if (m << sh) atomicOr(vbits + k, m << sh);
+                        if (sh && (m >> (32 - sh))) atomicOr(vbits + k + 1, m >> (32 - sh));
+                    }
+                }
+            }
         }
         __syncthreads();                                                   // res / stage are rewritten by the next stage
     }
@@ -231,17 +260,18 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const float* __restr
 
 using namespace ppnet;
 
-extern "C" int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int64_t n_maps, const float* segs_xy,
-                                   int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, uint8_t* verdict,
-                                   int32_t* first_hit, void* stream) {
+template <typename TS>
+static int launch_dda(const uint32_t* bits, int32_t resolution, int64_t n_maps, const TS* segs, int64_t n_segs,
+                      const int64_t* seg_off, int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit, uint32_t* vbits,
+                      void* stream) {
     PPNET_REQUIRE(n_maps >= 0 && n_segs >= 0 && resolution > 0, "dda: bad sizes");
     if (n_maps == 0 || n_segs == 0) return PPNET_OK;
-    PPNET_REQUIRE(bits && segs_xy && verdict, "dda: null pointer");
+    PPNET_REQUIRE(bits && segs && (verdict || vbits), "dda: null pointer");
     PPNET_REQUIRE(seg_off || segs_per_map * n_maps == n_segs, "dda: bad uniform grouping");
     PPNET_REQUIRE(seg_off == nullptr || segs_per_map > 0, "dda: pass the longest row in segs_per_map with a CSR");
     const int W = (resolution + 31) / 32;
     const size_t bm_bytes = (size_t)resolution * W * 4;
-    PPNET_REQUIRE((reinterpret_cast<uintptr_t>(bits) & 15) == 0 && (reinterpret_cast<uintptr_t>(segs_xy) & 15) == 0,
+    PPNET_REQUIRE((reinterpret_cast<uintptr_t>(bits) & 15) == 0 && (reinterpret_cast<uintptr_t>(segs) & 15) == 0,
                   "dda: bits and segs must be 16-byte aligned");
     const size_t smem = ((bm_bytes + 15) & ~(size_t)15) + 16 + (size_t)kDdaStage * (16 + 2 + 4);
     PPNET_REQUIRE(smem <= 220 * 1024, "dda: resolution too large for a shared-memory bitmap");
@@ -249,11 +279,28 @@ extern "C" int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int
     const int chunk = bm_bytes >= 64 * 1024 ? 8192 : kDdaStage;
     const int64_t chunks = (segs_per_map + chunk - 1) / chunk;
     PPNET_REQUIRE(chunks <= 65535, "dda: too many segments in one map");
+    cudaStream_t st = (cudaStream_t)stream;
+    // a 32-segment flush group owns its output word when every row starts on a multiple of 32
+    const int exclusive = (seg_off == nullptr && segs_per_map % 32 == 0) ? 1 : 0;
+    if (vbits && !exclusive) PPNET_CUDA(cudaMemsetAsync(vbits, 0, 4 * (size_t)((n_segs + 31) / 32), st));
     if (smem > 48 * 1024)
-        PPNET_CUDA(cudaFuncSetAttribute(dda_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPNET_CUDA(cudaFuncSetAttribute(dda_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)n_maps, (unsigned)chunks);
-    dda_kernel<<<grid, kDdaThreads, smem, (cudaStream_t)stream>>>(bits, resolution, W, segs_xy, seg_off, segs_per_map,
-                                                                  chunk, verdict, first_hit);
+    dda_kernel<TS><<<grid, kDdaThreads, smem, st>>>(bits, resolution, W, segs, seg_off, segs_per_map, chunk, verdict, first_hit,
+                                                    vbits, exclusive);
     PPNET_LAUNCH_CHECK("dda_kernel");
     return PPNET_OK;
+}
+
+extern "C" int ppnet_dda_gridcheck(const uint32_t* bits, int32_t resolution, int64_t n_maps, const float* segs_xy,
+                                   int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, uint8_t* verdict,
+                                   int32_t* first_hit, void* stream) {
+    PPNET_REQUIRE(verdict || n_segs == 0 || n_maps == 0, "dda: verdict is null");
+    return launch_dda<float>(bits, resolution, n_maps, segs_xy, n_segs, seg_off, segs_per_map, verdict, first_hit, nullptr, stream);
+}
+
+extern "C" int ppnet_dda_gridcheck_rc64(const uint32_t* bits, int32_t resolution, int64_t n_maps, const double* segs_rc,
+                                        int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, uint8_t* verdict,
+                                        int32_t* first_hit, uint32_t* vbits, void* stream) {
+    return launch_dda<double>(bits, resolution, n_maps, segs_rc, n_segs, seg_off, segs_per_map, verdict, first_hit, vbits, stream);
 }

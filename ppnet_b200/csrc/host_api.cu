@@ -11,7 +11,7 @@
 
 namespace ppnet {
 
-constexpr int kSlotBufs = 12;
+constexpr int kSlotBufs = 12;   // see generate_host_run for the buffer ids
 struct Slot {
     cudaStream_t st = nullptr;
     void* buf[kSlotBufs] = {};
@@ -24,6 +24,7 @@ struct Ctx {
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     unsigned long long* pinned_cnt = nullptr;    // pinned staging for per-slice counters: a device->host copy into
     size_t pinned_cap = 0;                       // pageable memory would block the issuing thread and serialise slices
+    cudaEvent_t ev[2] = {nullptr, nullptr};      // "slice's counts have landed" per slot
 };
 
 static int slot_reserve(Slot& s, int i, size_t bytes) {
@@ -138,6 +139,7 @@ extern "C" int ppnet_ctx_destroy(void* ctx) {
     cudaSetDevice(c->device);
     if (c->pinned_cnt) cudaFreeHost(c->pinned_cnt);
     for (int i = 0; i < 2; ++i) {
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         if (c->slot[i].st) { cudaStreamSynchronize(c->slot[i].st); cudaStreamDestroy(c->slot[i].st); }
         for (int j = 0; j < kSlotBufs; ++j) if (c->slot[i].buf[j]) cudaFree(c->slot[i].buf[j]);
     }
@@ -268,31 +270,50 @@ extern "C" int ppnet_bank_free(void* bank) {
 
 // `p` carries the generation settings and HOST output pointers (bank_* / in_* fields are ignored: the bank
 // comes from `bank`, draws from Philox).  Maps are produced in slices on two streams: slice k's device->host
-// copies overlap slice k+1's host->device copies and kernels.  With `io`, every slice also uploads its candidate
-// segments and runs the verdict kernels against the maps it has just generated -- the obstacle sets and bitmaps
-// never leave the device in between (ppnet_generate_and_check_host).
-static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const ppnet_pipeline_io* io) {
-    PPNET_REQUIRE(c && b && p, "generate_maps_host: null argument");
-    PPNET_REQUIRE(p->n_maps >= 0, "generate_maps_host: negative n_maps");
-    PPNET_REQUIRE(!p->in_angle && !p->in_trans && !p->in_cand, "generate_maps_host: caller-supplied draws need the device API");
+// copies overlap slice k+1's host->device copies and kernels.  With `io`, every slice also uploads (or draws on the
+// device) its candidate segments and runs the verdict kernels against the maps it has just generated -- the obstacle
+// sets and bitmaps never leave the device in between (ppnet_generate_and_check_host).
+//
+// One-array mode (io->segs_xy_f32 == NULL): ONE float64 upload per segment feeds all three verdicts -- the fused
+// A11 + A12 kernel and the DDA read it directly and apply the float32 cast + swap themselves; verdicts come back
+// bit-packed and / or as bytes; the survivors (free segments, valid maps) are compacted on the device and only
+// `count` indices travel.  Their counts are known one slice late, so slice k's index lists are copied after slice
+// k+1's kernels have been enqueued (the device never waits for the host).
+static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const ppnet_pipeline_io* io) {
     const int64_t spm = io ? io->segs_per_map : 0;
+    const bool propose = io && !io->segs_rc_f64 && io->propose_sigma > 0.0;
+    const bool one_array = io && !io->segs_xy_f32;
+    const bool want_bits_out = io && (io->vbits_f64 || io->vbits_f32 || io->vbits_dda);
+    const bool want_free = io && io->free_idx && io->free_count;
+    const bool want_valid = io && io->valid_idx && io->valid_count;
+    const bool any64 = io && (io->verdict_f64 || io->vbits_f64), any32 = io && (io->verdict_f32 || io->vbits_f32);
+    const bool anydda = io && (io->verdict_dda || io->vbits_dda);
     if (io) {
         PPNET_REQUIRE(spm > 0, "generate_and_check_host: segs_per_map must be positive");
-        PPNET_REQUIRE((io->verdict_f64 == nullptr) || io->segs_rc_f64, "generate_and_check_host: verdict_f64 needs segs_rc_f64");
-        PPNET_REQUIRE((io->verdict_f32 == nullptr && io->verdict_dda == nullptr) || io->segs_xy_f32,
-                      "generate_and_check_host: verdict_f32 / verdict_dda need segs_xy_f32");
+        PPNET_REQUIRE(!(io->segs_rc_f64 && io->propose_sigma > 0.0), "generate_and_check_host: segs_rc_f64 and propose_sigma are exclusive");
+        PPNET_REQUIRE(!any64 || io->segs_rc_f64 || propose, "generate_and_check_host: the A11 verdict needs segs_rc_f64 (or a device proposal)");
+        PPNET_REQUIRE(!(any32 || anydda) || io->segs_xy_f32 || io->segs_rc_f64 || propose,
+                      "generate_and_check_host: the A12 / DDA verdicts need segments");
+        PPNET_REQUIRE(one_array || !(want_bits_out || want_free),
+                      "generate_and_check_host: bit-packed verdicts / survivor lists need the one-array mode (segs_xy_f32 == NULL)");
+        PPNET_REQUIRE(!propose || one_array, "generate_and_check_host: a device proposal excludes segs_xy_f32");
+        PPNET_REQUIRE(!io->out_segs_rc || propose, "generate_and_check_host: out_segs_rc is the output of a device proposal");
+        PPNET_REQUIRE(!want_free || any64 || any32 || anydda, "generate_and_check_host: free_idx needs at least one verdict");
+        PPNET_REQUIRE((io->free_idx == nullptr) == (io->free_count == nullptr) && (io->valid_idx == nullptr) == (io->valid_count == nullptr),
+                      "generate_and_check_host: index lists come with their counts");
+        PPNET_REQUIRE(p->n_maps * spm <= 2147483647LL, "generate_and_check_host: more than 2^31 segments in one call");
     }
-    PPNET_CUDA(cudaSetDevice(c->device));
     const int R = (int)p->resolution, W = (R + 31) / 32;
     const int64_t O = p->obstacles_num, oo = O + b->pomax;
     const int64_t kSlice = io ? 1024 : 2048;
     // per-map byte sizes of the outputs, slot buffer ids: 0 pathpt, 1 segpt, 2 obs, 3 bits, 4 small ints, 5 counters,
-    // 6 segments f64, 7 segments f32, 8 / 9 / 10 verdicts
+    // 6 segments f64, 7 segments f32, 8 / 9 / 10 verdict bytes, 11 verdict words x3 + lists + workspace
     const size_t b_pp = sizeof(double) * 2 * (size_t)b->np, b_sp = sizeof(double) * 2 * (size_t)b->nseg1;
     const size_t b_ob = sizeof(double) * 3 * (size_t)oo, b_bt = (size_t)R * W * 4;
     const size_t b_small = 8 /*angle*/ + 8 /*trans*/ + 4 * 3 /*obs_cnt, rand_cnt, tries*/ + 4 /*valid, padded*/;
     const int64_t n_slices = (p->n_maps + kSlice - 1) / kSlice;
-    const size_t cnt_words = 4 * (size_t)std::max<int64_t>(n_slices, 1);
+    // pinned staging per slice: 4 generator counters + free count + valid count (6 words, padded to 8)
+    const size_t cnt_words = 8 * (size_t)std::max<int64_t>(n_slices, 1);
     if (c->pinned_cap < cnt_words) {
         if (c->pinned_cnt) cudaFreeHost(c->pinned_cnt);
         c->pinned_cnt = nullptr; c->pinned_cap = 0;
@@ -301,12 +322,47 @@ static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const 
     }
     unsigned long long* cnt_keep = c->pinned_cnt;
     for (size_t i = 0; i < cnt_words; ++i) cnt_keep[i] = 0ull;
-    const bool need_bits = p->out_bits || (io && io->verdict_dda);
-    int k = 0;
+    for (int i = 0; i < 2; ++i)
+        if (!c->ev[i]) PPNET_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+    const bool need_bits = p->out_bits || anydda;
+    const bool dev_words = one_array && (want_bits_out || want_free);
+    int64_t free_total = 0, valid_total = 0;
+
+    // second half of a slice: its index lists, once its counts have landed in the pinned staging area
+    auto finish_lists = [&](int64_t k) -> int {
+        if (!want_free && !want_valid) return PPNET_OK;
+        Slot& s = c->slot[k & 1];
+        PPNET_CUDA(cudaEventSynchronize(c->ev[k & 1]));
+        const int64_t nm = std::min(kSlice, p->n_maps - k * kSlice), ns = nm * spm;
+        const size_t words = (size_t)((ns + 31) / 32);
+        char* wbase = (char*)s.buf[11];
+        if (want_free) {
+            const int64_t cnt = (int64_t)cnt_keep[8 * k + 4];
+            const int32_t* d_idx = (const int32_t*)(wbase + 3 * 4 * words + 64);
+            if (cnt > 0) {
+                PPNET_CUDA(cudaMemcpyAsync(io->free_idx + free_total, d_idx, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s.st));
+                c->d2h_bytes += 4 * cnt;
+            }
+            free_total += cnt;
+        }
+        if (want_valid) {
+            const int64_t cnt = (int64_t)cnt_keep[8 * k + 5];
+            const int32_t* d_idx = (const int32_t*)(wbase + 3 * 4 * words + 64 + (want_free ? 4 * (size_t)ns : 0));
+            if (cnt > 0) {
+                PPNET_CUDA(cudaMemcpyAsync(io->valid_idx + valid_total, d_idx, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s.st));
+                c->d2h_bytes += 4 * cnt;
+            }
+            valid_total += cnt;
+        }
+        return PPNET_OK;
+    };
+
+    int64_t k = 0;
     for (int64_t m0 = 0; m0 < p->n_maps; m0 += kSlice, ++k) {
         Slot& s = c->slot[k & 1];
         const int64_t nm = std::min(kSlice, p->n_maps - m0);
         const int64_t ns = nm * spm;
+        const size_t words = (size_t)((ns + 31) / 32);
         int rc;
         if ((rc = slot_reserve(s, 0, b_pp * nm)) != PPNET_OK) return rc;
         if ((rc = slot_reserve(s, 1, b_sp * nm + 16)) != PPNET_OK) return rc;
@@ -315,14 +371,21 @@ static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const 
         if ((rc = slot_reserve(s, 4, b_small * nm + 64)) != PPNET_OK) return rc;
         if ((rc = slot_reserve(s, 5, 64)) != PPNET_OK) return rc;
         if (io) {
-            if (io->segs_rc_f64 && (rc = slot_reserve(s, 6, 32 * (size_t)ns)) != PPNET_OK) return rc;
+            if ((io->segs_rc_f64 || propose) && (rc = slot_reserve(s, 6, 32 * (size_t)ns)) != PPNET_OK) return rc;
             if (io->segs_xy_f32 && (rc = slot_reserve(s, 7, 16 * (size_t)ns)) != PPNET_OK) return rc;
             for (int v = 8; v <= 10; ++v)
                 if ((rc = slot_reserve(s, v, (size_t)ns)) != PPNET_OK) return rc;
+            // words x3 | counts (64 B) | free list | valid list | compaction workspace
+            const size_t ws_elems = (size_t)ppnet_compact_bits_workspace_elems(ns);
+            if ((rc = slot_reserve(s, 11, 3 * 4 * words + 64 + (want_free ? 4 * (size_t)ns : 0) + 4 * (size_t)nm + 64 + 8 * ws_elems)) != PPNET_OK)
+                return rc;
             // the segment uploads go first: they overlap the previous slice's kernels and downloads
             if (io->segs_rc_f64) {
                 PPNET_CUDA(cudaMemcpyAsync(s.buf[6], io->segs_rc_f64 + 4 * m0 * spm, 32 * (size_t)ns, cudaMemcpyHostToDevice, s.st));
                 c->h2d_bytes += 32 * ns;
+            } else if (propose) {
+                if ((rc = ppnet_propose_segments(p->seed, (uint64_t)(p->map0 + m0), nm, spm, p->resolution, io->propose_sigma,
+                                                 (double*)s.buf[6], (void*)s.st)) != PPNET_OK) return rc;
             }
             if (io->segs_xy_f32) {
                 PPNET_CUDA(cudaMemcpyAsync(s.buf[7], io->segs_xy_f32 + 4 * m0 * spm, 16 * (size_t)ns, cudaMemcpyHostToDevice, s.st));
@@ -350,7 +413,35 @@ static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const 
         q.out_tries = d_tries; q.out_valid = d_valid;
         q.counters = (unsigned long long*)s.buf[5];
         if ((rc = ppnet_generate_maps(&q, (void*)s.st)) != PPNET_OK) return rc;
-        if (io) {
+        char* wbase = io ? (char*)s.buf[11] : nullptr;
+        uint32_t* w64 = (uint32_t*)wbase;
+        uint32_t* w32 = (uint32_t*)(wbase + 4 * words);
+        uint32_t* wdd = (uint32_t*)(wbase + 8 * words);
+        int64_t* d_counts = (int64_t*)(wbase + 12 * words);                   // [0] free, [1] valid (64 B, 8-aligned: words*12 % 8 == 0 or 4)
+        if (io && ((12 * words) & 7)) d_counts = (int64_t*)(wbase + 12 * words + 4);
+        int32_t* d_free = (int32_t*)(wbase + 12 * words + 64);
+        int32_t* d_vidx = (int32_t*)(wbase + 12 * words + 64 + (want_free ? 4 * (size_t)ns : 0));
+        int64_t* d_ws = (int64_t*)(((uintptr_t)(d_vidx + nm) + 63) & ~(uintptr_t)63);
+        if (io && one_array) {
+            if ((any64 || any32) &&
+                (rc = ppnet_verdict_fused((const double*)s.buf[6], ns, nullptr, spm, nm, (const double*)s.buf[2], d_ocnt, (int32_t)oo,
+                                          io->clearance_px, io->bound, io->dot_mode, io->cmp_mode,
+                                          io->verdict_f64 ? (uint8_t*)s.buf[8] : nullptr, io->verdict_f32 ? (uint8_t*)s.buf[9] : nullptr,
+                                          (any64 && dev_words) ? w64 : nullptr, (any32 && dev_words) ? w32 : nullptr,
+                                          (void*)s.st)) != PPNET_OK) return rc;
+            if (anydda &&
+                (rc = ppnet_dda_gridcheck_rc64((const uint32_t*)s.buf[3], R, nm, (const double*)s.buf[6], ns, nullptr, spm,
+                                               io->verdict_dda ? (uint8_t*)s.buf[10] : nullptr, nullptr, dev_words ? wdd : nullptr,
+                                               (void*)s.st)) != PPNET_OK) return rc;
+            if (want_free) {
+                const uint32_t* arr[3]; int na = 0;
+                if (any64) arr[na++] = w64;
+                if (any32) arr[na++] = w32;
+                if (anydda) arr[na++] = wdd;
+                if ((rc = ppnet_compact_bits(arr[0], na > 1 ? arr[1] : nullptr, na > 2 ? arr[2] : nullptr, ns, (int32_t)(m0 * spm), d_free,
+                                             d_counts, d_ws, (void*)s.st)) != PPNET_OK) return rc;
+            }
+        } else if (io) {
             if (io->verdict_f64 &&
                 (rc = ppnet_segcheck_edage_f64((const double*)s.buf[6], ns, nullptr, spm, nm, (const double*)s.buf[2], d_ocnt,
                                                (int32_t)oo, io->clearance_px, io->bound, io->dot_mode, (uint8_t*)s.buf[8],
@@ -363,11 +454,20 @@ static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const 
                 (rc = ppnet_dda_gridcheck((const uint32_t*)s.buf[3], R, nm, (const float*)s.buf[7], ns, nullptr, spm,
                                           (uint8_t*)s.buf[10], nullptr, (void*)s.st)) != PPNET_OK) return rc;
         }
+        if (want_valid &&
+            (rc = ppnet_compact_u8_i32(d_valid, nm, 1, (int32_t)m0, d_vidx, d_counts + 1, (void*)s.st)) != PPNET_OK) return rc;
 #define PPNET_D2H(host, devp, bytes)                                                                        \
     if (host) {                                                                                             \
         PPNET_CUDA(cudaMemcpyAsync((char*)(host), devp, (bytes), cudaMemcpyDeviceToHost, s.st));            \
         c->d2h_bytes += (int64_t)(bytes);                                                                   \
     }
+        if (want_free || want_valid) {          // the counts first: the host needs them to size the list copies
+            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 8 * k + 4, d_counts, 16, cudaMemcpyDeviceToHost, s.st));
+            c->d2h_bytes += 16;
+        }
+        if (p->counters)
+            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 8 * k, s.buf[5], 32, cudaMemcpyDeviceToHost, s.st));
+        PPNET_CUDA(cudaEventRecord(c->ev[k & 1], s.st));
         PPNET_D2H(p->out_pathpt ? (char*)p->out_pathpt + b_pp * m0 : nullptr, s.buf[0], b_pp * nm);
         PPNET_D2H(p->out_segpt ? (char*)p->out_segpt + b_sp * m0 : nullptr, s.buf[1], b_sp * nm);
         PPNET_D2H(p->out_obs ? (char*)p->out_obs + b_ob * m0 : nullptr, s.buf[2], b_ob * nm);
@@ -382,16 +482,39 @@ static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const 
             PPNET_D2H(io->verdict_f64 ? io->verdict_f64 + m0 * spm : nullptr, s.buf[8], (size_t)ns);
             PPNET_D2H(io->verdict_f32 ? io->verdict_f32 + m0 * spm : nullptr, s.buf[9], (size_t)ns);
             PPNET_D2H(io->verdict_dda ? io->verdict_dda + m0 * spm : nullptr, s.buf[10], (size_t)ns);
+            // slices start on word boundaries: kSlice * spm is a multiple of 32
+            PPNET_D2H(io->vbits_f64 ? io->vbits_f64 + (m0 * spm) / 32 : nullptr, w64, 4 * words);
+            PPNET_D2H(io->vbits_f32 ? io->vbits_f32 + (m0 * spm) / 32 : nullptr, w32, 4 * words);
+            PPNET_D2H(io->vbits_dda ? io->vbits_dda + (m0 * spm) / 32 : nullptr, wdd, 4 * words);
+            PPNET_D2H(io->out_segs_rc ? io->out_segs_rc + 4 * m0 * spm : nullptr, s.buf[6], 32 * (size_t)ns);
         }
-        if (p->counters)
-            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 4 * k, s.buf[5], 32, cudaMemcpyDeviceToHost, s.st));
+        if (k > 0 && (rc = finish_lists(k - 1)) != PPNET_OK) return rc;
     }
+    if (k > 0) { int rc = finish_lists(k - 1); if (rc != PPNET_OK) return rc; }
     PPNET_CUDA(cudaStreamSynchronize(c->slot[0].st));
     PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
     if (p->counters)
         for (int64_t q = 0; q < n_slices; ++q)
-            for (int i = 0; i < 4; ++i) p->counters[i] += cnt_keep[4 * q + i];
+            for (int i = 0; i < 4; ++i) p->counters[i] += cnt_keep[8 * q + i];
+    if (want_free) *io->free_count = free_total;
+    if (want_valid) *io->valid_count = valid_total;
     return PPNET_OK;
+}
+
+static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const ppnet_pipeline_io* io) {
+    PPNET_REQUIRE(c && b && p, "generate_maps_host: null argument");
+    PPNET_REQUIRE(p->n_maps >= 0, "generate_maps_host: negative n_maps");
+    PPNET_REQUIRE(!p->in_angle && !p->in_trans && !p->in_cand, "generate_maps_host: caller-supplied draws need the device API");
+    PPNET_CUDA(cudaSetDevice(c->device));
+    const int rc = generate_host_run(c, b, p, io);
+    if (rc != PPNET_OK) {
+        // copies into the caller's buffers may still be in flight on both streams: let them land before the caller
+        // sees the error (and possibly frees those buffers)
+        cudaStreamSynchronize(c->slot[0].st);
+        cudaStreamSynchronize(c->slot[1].st);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* p) {

@@ -22,7 +22,9 @@ extern "C" const char* ppnet_last_error(void) { return ppnet::g_err; }
 extern "C" int ppnet_version(void) { return 100; }
 extern "C" int64_t ppnet_launch_count(void) { return ppnet::g_launches.load(); }
 
-// struct layout guard for ctypes / cgo / JNI mirrors: 0 -> sizeof(ppnet_gen_params), 1 -> sizeof(ppnet_path_params)
+// struct layout guard for ctypes / cgo / JNI mirrors: 0 -> sizeof(ppnet_gen_params), 1 -> sizeof(ppnet_path_params),
+// 2 -> sizeof(ppnet_pipeline_io)
 extern "C" int64_t ppnet_sizeof_params(int32_t which) {
-    return which == 0 ? (int64_t)sizeof(ppnet_gen_params) : which == 1 ? (int64_t)sizeof(ppnet_path_params) : -1;
+    return which == 0 ? (int64_t)sizeof(ppnet_gen_params) : which == 1 ? (int64_t)sizeof(ppnet_path_params)
+           : which == 2 ? (int64_t)sizeof(ppnet_pipeline_io) : -1;
 }

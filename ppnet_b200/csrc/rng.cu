@@ -124,9 +124,43 @@ gmm_sample_kernel(uint2 key, uint64_t sample0, int64_t n, int K, int D, const fl
     }
 }
 
+// Candidate segments of map g (the workload SURVEY 8(d) config 2 describes: s ~ U(0, R)^2, e = s + N(0, sigma^2) per
+// axis), drawn on the device so that generator-mode callers upload nothing.  Segment k of map g is a pure function of
+// (seed, g, k): Philox block 2k -> start (two 53-bit uniforms), block 2k+1 -> Box-Muller offset in float64.
+__global__ void propose_segments_kernel(uint2 key, uint64_t map0, int64_t n_maps, int64_t spm, double R, double sigma,
+                                        double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_maps * spm) return;
+    const uint64_t g = map0 + (uint64_t)(t / spm);
+    const uint32_t k = (uint32_t)(t % spm);
+    const uint4 a = Philox::gen(key, make_uint4(2u * k, STREAM_SEGS, (uint32_t)g, (uint32_t)(g >> 32)));
+    const uint4 b = Philox::gen(key, make_uint4(2u * k + 1u, STREAM_SEGS, (uint32_t)g, (uint32_t)(g >> 32)));
+    const double s0 = __dmul_rn(u53(a.x, a.y), R), s1 = __dmul_rn(u53(a.z, a.w), R);
+    const double u1 = u53(b.x, b.y) + (1.0 / 9007199254740992.0);          // (0, 1]
+    const double rad = __dmul_rn(sqrt(-2.0 * log(u1)), sigma);
+    double sn, cs;
+    sincospi(2.0 * u53(b.z, b.w), &sn, &cs);
+    double2* o = reinterpret_cast<double2*>(out + 4 * t);
+    o[0] = make_double2(s0, s1);
+    o[1] = make_double2(__dadd_rn(s0, __dmul_rn(rad, cs)), __dadd_rn(s1, __dmul_rn(rad, sn)));
+}
+
 }  // namespace ppnet
 
 using namespace ppnet;
+
+extern "C" int ppnet_propose_segments(uint64_t seed, uint64_t map0, int64_t n_maps, int64_t segs_per_map, double resolution,
+                                      double sigma, double* segs_rc, void* stream) {
+    PPNET_REQUIRE(n_maps >= 0 && segs_per_map >= 0 && segs_per_map <= 1073741823LL, "propose_segments: bad sizes");
+    if (n_maps == 0 || segs_per_map == 0) return PPNET_OK;
+    PPNET_REQUIRE(segs_rc && (reinterpret_cast<uintptr_t>(segs_rc) & 15) == 0, "propose_segments: output must be 16-byte aligned");
+    const int64_t n = n_maps * segs_per_map;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    propose_segments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key, map0, n_maps, segs_per_map,
+                                                                                            resolution, sigma, segs_rc);
+    PPNET_LAUNCH_CHECK("propose_segments_kernel");
+    return PPNET_OK;
+}
 
 static inline uint2 make_key(uint64_t seed) { return make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); }
 

@@ -118,8 +118,11 @@ class PipelineIO(ctypes.Structure):
     """Mirror of `ppnet_pipeline_io` (include/ppnet_b200.h)."""
     _fields_ = [("segs_rc_f64", ctypes.c_void_p), ("segs_xy_f32", ctypes.c_void_p), ("segs_per_map", ctypes.c_int64),
                 ("clearance_px", ctypes.c_double), ("bound", ctypes.c_double), ("dot_mode", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("verdict_f64", ctypes.c_void_p), ("verdict_f32", ctypes.c_void_p),
-                ("verdict_dda", ctypes.c_void_p)]
+                ("cmp_mode", ctypes.c_int32), ("verdict_f64", ctypes.c_void_p), ("verdict_f32", ctypes.c_void_p),
+                ("verdict_dda", ctypes.c_void_p),
+                ("vbits_f64", ctypes.c_void_p), ("vbits_f32", ctypes.c_void_p), ("vbits_dda", ctypes.c_void_p),
+                ("free_idx", ctypes.c_void_p), ("free_count", ctypes.c_void_p), ("valid_idx", ctypes.c_void_p),
+                ("valid_count", ctypes.c_void_p), ("propose_sigma", ctypes.c_double), ("out_segs_rc", ctypes.c_void_p)]
 
 
 class HostBank:
@@ -151,22 +154,50 @@ class HostBank:
             pass
 
 
+def _out(a, dt, size, name):
+    """Caller-supplied output array: exact dtype, size and contiguity (it is handed to cudaMemcpyAsync as a raw pointer)."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dt) or not a.flags.c_contiguous or a.size != size:
+        raise PPNetError("%s must be a C-contiguous %s array with %d elements" % (name, np.dtype(dt), size))
+    if not a.flags.writeable:
+        raise PPNetError("%s must be writeable" % name)
+    return a
+
+
 def generate_maps_host(ctx, bank, map0, n_maps, reps, obstacles_num, out, resolution=224, map_size=50.0,
                        obstacle_size=5.0, clearance=1.0, seed=DEFAULT_SEED, max_tries=4096, raster_inflate=0.0, checks=None):
     """MapGenerate.generate into HOST arrays.  `out` is a dict of preallocated numpy arrays with any of the keys
     angle f64[n], trans i32[n,2], segpt f64[n,S+1,2], pathpt f64[n,Np,2], obs f64[n,O+pomax,3], obs_cnt i32[n],
     rand_cnt i32[n], bits u32[n,R,W], tries i32[n], valid u8[n], counters u64[4].
     `checks` (optional dict) fuses the verdicts on the fresh maps into the same call (ppnet_generate_and_check_host):
-    segs_rc_f64 f64[n*spm,4] and/or segs_xy_f32 f32[n*spm,4], clearance_px, bound, dot_mode, and any of the uint8
-    outputs verdict_f64 (A11), verdict_f32 (A12), verdict_dda."""
+      segments    segs_rc_f64 f64[n*spm,4]; optionally segs_xy_f32 f32[n*spm,4] (round-1 two-array mode).  Without
+                  segs_xy_f32 the float32 flavours run on the device-side cast + swap of segs_rc_f64 (one upload).
+                  Or propose_sigma > 0 with segs_per_map: the segments are drawn on the device, nothing is uploaded
+                  (out_segs_rc f64[n*spm,4] receives them if given).
+      settings    clearance_px, bound, dot_mode, cmp_mode
+      outputs     verdict_f64 / verdict_f32 / verdict_dda u8[n*spm]; vbits_f64 / vbits_f32 / vbits_dda
+                  u32[ceil(n*spm/32)] bit-packed; free_idx i32[n*spm] + free_count i64[1] (segments free under every
+                  requested verdict, ascending); valid_idx i32[n] + valid_count i64[1] (maps with a valid placement)."""
     p = GenParams()
     p.map0, p.n_maps, p.reps, p.obstacles_num, p.max_tries = map0, n_maps, reps, obstacles_num, max_tries
     p.resolution, p.map_size, p.obstacle_size = float(resolution), float(map_size), float(obstacle_size)
     p.clearance, p.raster_inflate, p.seed = float(clearance), float(raster_inflate), seed
+    R, W = int(resolution), (int(resolution) + 31) // 32
+    shapes = dict(angle=(np.float64, n_maps), trans=(np.int32, 2 * n_maps), segpt=(np.float64, 2 * bank.nseg1 * n_maps),
+                  pathpt=(np.float64, 2 * bank.np * n_maps), obs=(np.float64, 3 * (obstacles_num + bank.pomax) * n_maps),
+                  obs_cnt=(np.int32, n_maps), rand_cnt=(np.int32, n_maps), tries=(np.int32, n_maps), valid=(np.uint8, n_maps))
     for name in ("angle", "trans", "segpt", "pathpt", "obs", "obs_cnt", "rand_cnt", "bits", "tries", "valid"):
         a = out.get(name)
+        if a is not None:
+            if name == "bits":
+                if a.dtype not in (np.uint32, np.int32):
+                    raise PPNetError("bits must be a uint32 / int32 array")
+                _out(a, a.dtype, n_maps * R * W, "bits")
+            else:
+                _out(a, shapes[name][0], shapes[name][1], name)
         setattr(p, "out_" + name, a.ctypes.data if a is not None else None)
     cts = out.get("counters")
+    if cts is not None:
+        _out(cts, np.uint64, 4, "counters")
     p.counters = cts.ctypes.data if cts is not None else None
     if checks is None:
         check(lib().ppnet_generate_maps_host(ctx._h, bank._h, ctypes.byref(p)), "ppnet_generate_maps_host")
@@ -179,18 +210,30 @@ def generate_maps_host(ctx, bank, map0, n_maps, reps, obstacles_num, out, resolu
     if s32 is not None:
         s32 = _c(s32, np.float32, "segs_xy_f32")
         io.segs_xy_f32 = s32.ctypes.data
-    n_seg = (len(s64) if s64 is not None else len(s32)) if (s64 is not None or s32 is not None) else 0
-    if n_maps == 0 or n_seg % max(n_maps, 1):
-        raise PPNetError("segments must be uniformly grouped: len(segs) divisible by n_maps")
-    io.segs_per_map = n_seg // n_maps
+    if s64 is not None or s32 is not None:
+        n_seg = s64.size // 4 if s64 is not None else s32.size // 4
+        if s64 is not None and s32 is not None and s64.size != s32.size:
+            raise PPNetError("segs_rc_f64 and segs_xy_f32 must describe the same segments")
+        if n_maps == 0 or n_seg % max(n_maps, 1):
+            raise PPNetError("segments must be uniformly grouped: len(segs) divisible by n_maps")
+        io.segs_per_map = n_seg // n_maps
+    else:
+        io.propose_sigma = float(checks.get("propose_sigma", 0.0))
+        io.segs_per_map = int(checks.get("segs_per_map", 0))
+        if io.propose_sigma <= 0 or io.segs_per_map <= 0:
+            raise PPNetError("checks need segments: segs_rc_f64 / segs_xy_f32, or propose_sigma and segs_per_map")
+        n_seg = io.segs_per_map * n_maps
     io.clearance_px, io.bound, io.dot_mode = float(checks["clearance_px"]), float(checks.get("bound", DEFAULT_BOUND)), \
         int(checks.get("dot_mode", DOT_FUSED_SKX))
-    for name in ("verdict_f64", "verdict_f32", "verdict_dda"):
+    io.cmp_mode = int(checks.get("cmp_mode", 0))
+    n_words = (n_seg + 31) // 32
+    for name, dt, size in (("verdict_f64", np.uint8, n_seg), ("verdict_f32", np.uint8, n_seg), ("verdict_dda", np.uint8, n_seg),
+                           ("vbits_f64", np.uint32, n_words), ("vbits_f32", np.uint32, n_words), ("vbits_dda", np.uint32, n_words),
+                           ("free_idx", np.int32, n_seg), ("free_count", np.int64, 1), ("valid_idx", np.int32, n_maps),
+                           ("valid_count", np.int64, 1), ("out_segs_rc", np.float64, 4 * n_seg)):
         a = checks.get(name)
         if a is not None:
-            if a.dtype != np.uint8 or a.size != n_seg:
-                raise PPNetError("%s must be uint8[%d]" % (name, n_seg))
-            setattr(io, name, a.ctypes.data)
+            setattr(io, name, _out(a, dt, size, name).ctypes.data)
     check(lib().ppnet_generate_and_check_host(ctx._h, bank._h, ctypes.byref(p), ctypes.byref(io)),
           "ppnet_generate_and_check_host")
     return out

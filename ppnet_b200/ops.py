@@ -79,6 +79,42 @@ def segcheck_mpnet_f32(pts_xy, obs, obs_cnt, clearance, seg_off=None, bound=DEFA
     return (out, steer) if want_steer else out
 
 
+CMP_F32_NEP50, CMP_F64_NUMPY1 = 0, 1
+
+
+def verdict_fused(pts_rc, obs, obs_cnt, clearance, seg_off=None, bound=DEFAULT_BOUND, dot_mode=DOT_FUSED_SKX,
+                  cmp_mode=CMP_F32_NEP50, want=("bits64", "bits32"), out=None):
+    """A11 + A12 fused on one read of the f64 (row, col) segments (ppnet_verdict_fused).  The A12 flavour runs on
+    (x, y) = (float32(col), float32(row)).  `want` picks the outputs: "u8_64" / "u8_32" (uint8[N]) and "bits64" /
+    "bits32" (int32[ceil(N/32)], bit i & 31 of word i >> 5 = segment i).  -> dict of tensors (pass `out` to reuse)."""
+    _need(pts_rc, torch.float64, "pts_rc")
+    _need(obs, torch.float64, "obs")
+    _need(obs_cnt, torch.int32, "obs_cnt")
+    n, m, omax = pts_rc.shape[0], obs.shape[0], obs.shape[1]
+    so, spm = _seg_grouping(n, m, seg_off)
+    out = {} if out is None else out
+    for k in want:
+        if k not in ("u8_64", "u8_32", "bits64", "bits32"):
+            raise PPNetError("verdict_fused: unknown output %r" % (k,))
+        if k not in out:
+            out[k] = (torch.empty(n, dtype=torch.uint8, device=pts_rc.device) if k.startswith("u8") else
+                      torch.empty((n + 31) // 32, dtype=torch.int32, device=pts_rc.device))
+        _need(out[k], torch.uint8 if k.startswith("u8") else torch.int32, k)
+    g = lambda k: _ptr(out[k]) if k in want else ctypes.c_void_p(0)
+    check(lib().ppnet_verdict_fused(
+        _ptr(pts_rc), ctypes.c_int64(n), _ptr(so), ctypes.c_int64(spm), ctypes.c_int64(m), _ptr(obs), _ptr(obs_cnt),
+        ctypes.c_int32(omax), ctypes.c_double(clearance), ctypes.c_double(bound), ctypes.c_int32(dot_mode),
+        ctypes.c_int32(cmp_mode), g("u8_64"), g("u8_32"), g("bits64"), g("bits32"), _stream()), "ppnet_verdict_fused")
+    return out
+
+
+def unpack_bits(words, n):
+    """int32/uint32 words [ceil(n/32)] -> uint8[n] (torch, on the words' device): bit i & 31 of word i >> 5."""
+    w = words.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    sh = torch.arange(32, device=words.device, dtype=torch.int64)
+    return ((w[:, None] >> sh[None, :]) & 1).to(torch.uint8).reshape(-1)[:n]
+
+
 def path_feasible_f32(wp, path_off, path_map, obs, obs_cnt, clearance, bound=DEFAULT_BOUND):
     """feasibility_check batched (neuralplanner.py:96-102) -> (feasible u8[P], n_checked i32[P])."""
     _need(wp, torch.float32, "wp")
@@ -255,6 +291,33 @@ def dda_gridcheck(bits, resolution, segs_xy, seg_off=None, want_first=True, max_
                                     ctypes.c_int64(n), _ptr(so), ctypes.c_int64(spm), _ptr(v), _ptr(fh), _stream()),
           "ppnet_dda_gridcheck")
     return (v, fh) if want_first else v
+
+
+def dda_gridcheck_rc64(bits, resolution, segs_rc, seg_off=None, want=("bits",), max_segs_per_map=None, out=None):
+    """The DDA on the A11 array read directly (ppnet_dda_gridcheck_rc64): segs_rc f64[N,4] = (s_row, s_col, e_row,
+    e_col), walked as (x, y) = (float32(col), float32(row)).  `want`: any of "u8" (uint8[N]), "bits"
+    (int32[ceil(N/32)]), "first" (int32[N]).  -> dict of tensors."""
+    _need(bits, torch.int32, "bits")
+    _need(segs_rc, torch.float64, "segs_rc")
+    m, n = bits.shape[0], segs_rc.shape[0]
+    if seg_off is None:
+        so, spm = None, n // max(m, 1)
+    else:
+        so = _need(seg_off, torch.int64, "seg_off")
+        spm = max_segs_per_map if max_segs_per_map is not None else max(int((so[1:] - so[:-1]).max().item()), 1)
+    out = {} if out is None else out
+    shapes = {"u8": (n, torch.uint8), "bits": ((n + 31) // 32, torch.int32), "first": (n, torch.int32)}
+    for k in want:
+        if k not in shapes:
+            raise PPNetError("dda_gridcheck_rc64: unknown output %r" % (k,))
+        if k not in out:
+            out[k] = torch.empty(shapes[k][0], dtype=shapes[k][1], device=bits.device)
+        _need(out[k], shapes[k][1], k)
+    g = lambda k: _ptr(out[k]) if k in want else ctypes.c_void_p(0)
+    check(lib().ppnet_dda_gridcheck_rc64(_ptr(bits), ctypes.c_int32(resolution), ctypes.c_int64(m), _ptr(segs_rc),
+                                         ctypes.c_int64(n), _ptr(so), ctypes.c_int64(spm), g("u8"), g("first"), g("bits"),
+                                         _stream()), "ppnet_dda_gridcheck_rc64")
+    return out
 
 
 class GenParams(ctypes.Structure):
@@ -549,3 +612,50 @@ def compact_u8(flags, keep=0):
     check(L.ppnet_compact_u8(_ptr(flags), ctypes.c_int64(n), ctypes.c_uint8(keep), _ptr(idx), _ptr(cnt), _ptr(ws), _stream()),
           "ppnet_compact_u8")
     return idx, cnt
+
+
+def propose_segments(map0, n_maps, segs_per_map, resolution=224, sigma=15.0, seed=DEFAULT_SEED, out=None, device="cuda"):
+    """Device-side segment source (ppnet_propose_segments): the config-2 candidate segments of global maps
+    [map0, map0 + n_maps) -> f64[n_maps * segs_per_map, 4] (s_row, s_col, e_row, e_col), a pure function of
+    (seed, global map index, k)."""
+    n = n_maps * segs_per_map
+    out = torch.empty([n, 4], dtype=torch.float64, device=device) if out is None else _need(out, torch.float64, "out")
+    check(lib().ppnet_propose_segments(ctypes.c_uint64(seed), ctypes.c_uint64(map0), ctypes.c_int64(n_maps),
+                                       ctypes.c_int64(segs_per_map), ctypes.c_double(resolution), ctypes.c_double(sigma),
+                                       _ptr(out), _stream()), "ppnet_propose_segments")
+    return out
+
+
+def compact_u8_i32(flags, keep=1, idx_base=0):
+    """One-CTA ordered compaction of a short flag array (ppnet_compact_u8_i32) -> (idx i32[n], count i64[1])."""
+    _need(flags, torch.uint8, "flags")
+    n = flags.numel()
+    idx = torch.empty([n], dtype=torch.int32, device=flags.device)
+    cnt = torch.empty([1], dtype=torch.int64, device=flags.device)
+    check(lib().ppnet_compact_u8_i32(_ptr(flags), ctypes.c_int64(n), ctypes.c_uint8(keep), ctypes.c_int32(idx_base), _ptr(idx),
+                                     _ptr(cnt), _stream()), "ppnet_compact_u8_i32")
+    return idx, cnt
+
+
+def compact_bits(a, b=None, c=None, n=None, out=None, idx_base=0):
+    """Ordered compaction of bit-packed verdicts (ppnet_compact_bits): survivors = segments whose bit is clear in every
+    given array -> (idx i32[n] (first `count` valid, ascending), count i64[1]) on the device."""
+    _need(a, torch.int32, "a")
+    for t, nm in ((b, "b"), (c, "c")):
+        if t is not None:
+            _need(t, torch.int32, nm)
+            if t.numel() != a.numel():
+                raise PPNetError("compact_bits: arrays must have the same number of words")
+    n = a.numel() * 32 if n is None else int(n)
+    if (n + 31) // 32 != a.numel():
+        raise PPNetError("compact_bits: n does not match the number of words")
+    L = lib()
+    L.ppnet_compact_bits_workspace_elems.restype = ctypes.c_int64
+    if out is None:
+        out = (torch.empty([n], dtype=torch.int32, device=a.device), torch.empty([1], dtype=torch.int64, device=a.device),
+               torch.empty([int(L.ppnet_compact_bits_workspace_elems(ctypes.c_int64(n)))], dtype=torch.int64, device=a.device))
+    idx, cnt, ws = out
+    check(L.ppnet_compact_bits(_ptr(a), _ptr(b), _ptr(c), ctypes.c_int64(n), ctypes.c_int32(idx_base), _ptr(idx), _ptr(cnt),
+                               _ptr(ws), _stream()),
+          "ppnet_compact_bits")
+    return idx, cnt, ws

@@ -66,6 +66,8 @@ def test_parameter_struct_layouts_match_the_library():
     L.ppnet_sizeof_params.restype = ctypes.c_int64
     assert L.ppnet_sizeof_params(ctypes.c_int32(0)) == ctypes.sizeof(ops.GenParams)
     assert L.ppnet_sizeof_params(ctypes.c_int32(1)) == ctypes.sizeof(ops.PathParams)
+    from ppnet_b200 import host
+    assert L.ppnet_sizeof_params(ctypes.c_int32(2)) == ctypes.sizeof(host.PipelineIO)
 
 
 def test_new_entry_points_validate_before_touching_cuda():
