@@ -226,6 +226,7 @@ typedef struct ppnet_path_params {
     int32_t max_obst_iter;         /* A9 guard per isle (the reference loops until it succeeds)                 */
     int32_t max_obst_rand;         /* row length of in_obst_rand                                                */
     double clearance, map_size, resolution;
+    double width_coef;             /* Path.search_isle(width_coef): isle depth threshold, reference default 0.2 */
     uint64_t seed;
     /* optional caller-supplied draws (parity mode); NULL -> Philox keyed by the global path id                 */
     const uint8_t* force_straight; /* [n]        PathGroup's 1 % forced-straight flag                           */
@@ -284,7 +285,8 @@ typedef struct ppnet_path_params {
     double* obs;                   /* [n][pomax][3] Path.obstacles [x, y, r]                                    */
     int32_t* obs_cnt;              /* [n]                                                                       */
     int32_t* obst_rand_used;       /* [n]        torch.rand(1) draws consumed                                   */
-    int32_t* status;               /* [n] bit0: max_obst_iter hit, bit1: supplied draws exhausted, bit2: pomax overflow */
+    int32_t* status;               /* [n] bit0: max_obst_iter hit, bit1: supplied draws exhausted, bit2: pomax overflow,
+                                      bit3: hull / isle capacity (hmax) overflow -- the bank entry is unusable           */
 } ppnet_path_params;
 int ppnet_path_synthesize(const ppnet_path_params* params, void* stream);
 
@@ -329,6 +331,13 @@ int ppnet_compact_u8_i32(const uint8_t* flags, int64_t n, uint8_t keep, int32_t 
  *      bytes and generator-mode callers upload nothing.                                                          */
 int ppnet_propose_segments(uint64_t seed, uint64_t map0, int64_t n_maps, int64_t segs_per_map, double resolution,
                            double sigma, double* segs_rc, void* stream);
+
+/* ---- 64-bit content digest of per-map arrays (cross-rank identity proof): *acc += sum over units u and 32-bit words k
+ *      of mix(word ^ mix(mix(global_unit_index, salt) + k)) modulo 2^64 -- additive over any split of the unit range.
+ *      data[n_units][words_per_unit] uint32 (any dtype viewed as words); with rows != NULL only the first
+ *      rows[u] * row_words words of unit u count.  acc is a DEVICE uint64.                                         */
+int ppnet_digest_u32(const uint32_t* data, int64_t words_per_unit, int64_t n_units, uint64_t unit0,
+                     const int32_t* rows, int32_t row_words, uint64_t salt, uint64_t* acc, void* stream);
 
 /* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
 int ppnet_ctx_create(int32_t device, void** ctx);

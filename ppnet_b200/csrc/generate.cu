@@ -177,7 +177,10 @@ generate_kernel(ppnet_gen_params P) {
         int tries = 0;
         double angle = 0.0;
         int t0 = 0, t1 = 0;
-        if (P.in_angle) {                                 // parity mode: the caller supplies the draws
+        if (P.bank_hull_cnt[j] > P.hmax) {
+            // the bank's hull was truncated (ppnet_hull2d_i32 reports the true vertex count): a placement test on a partial
+            // hull could accept a path that leaves the image, so the map is flagged invalid (tries = 0) instead
+        } else if (P.in_angle) {                          // parity mode: the caller supplies the draws
             angle = P.in_angle[lm];
             t0 = P.in_trans[2 * lm];
             t1 = P.in_trans[2 * lm + 1];

@@ -5,6 +5,10 @@
 // slice k-1's device->host copy (double buffering).  Host buffers may be pageable (copies then stage
 // through the driver) or pinned (cudaHostRegister / torch pin_memory -- true async DMA).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -24,13 +28,22 @@ struct Ctx {
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     unsigned long long* pinned_cnt = nullptr;    // pinned staging for per-slice counters: a device->host copy into
     size_t pinned_cap = 0;                       // pageable memory would block the issuing thread and serialise slices
-    cudaEvent_t ev[2] = {nullptr, nullptr};      // "slice's counts have landed" per slot
+    char* pinned_small = nullptr;                // pinned staging for the small per-map outputs (one copy per slice
+    size_t pinned_small_cap = 0;                 // instead of six tiny ones: a tiny DMA costs ~6 us of engine time)
+    // generate / generate-and-check pipeline: one stream per direction + one for the kernels, kPipe slices in flight.
+    // Uploads run back to back on st_up and downloads back to back on st_down (each PCIe direction stays busy), the
+    // kernels of slice k wait for its upload, its download waits for its kernels; events guard the reuse of a slot.
+    static constexpr int kPipe = 3;
+    Slot pslot[kPipe];                           // buffers only (their .st stays null)
+    cudaStream_t st_up = nullptr, st_cmp = nullptr, st_down = nullptr;
+    cudaEvent_t ev_up[kPipe] = {}, ev_cmp[kPipe] = {}, ev_cnt[kPipe] = {}, ev_down[kPipe] = {};
 };
 
 static int slot_reserve(Slot& s, int i, size_t bytes) {
     if (bytes <= s.cap[i]) return PPNET_OK;
     if (s.buf[i]) {
-        PPNET_CUDA(cudaStreamSynchronize(s.st));
+        if (s.st) PPNET_CUDA(cudaStreamSynchronize(s.st));
+        else PPNET_CUDA(cudaDeviceSynchronize());          // pipeline slots are shared by three streams
         PPNET_CUDA(cudaFree(s.buf[i]));
         s.buf[i] = nullptr;
         s.cap[i] = 0;
@@ -138,8 +151,14 @@ extern "C" int ppnet_ctx_destroy(void* ctx) {
     if (!c) return PPNET_OK;
     cudaSetDevice(c->device);
     if (c->pinned_cnt) cudaFreeHost(c->pinned_cnt);
+    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    for (cudaStream_t st : {c->st_up, c->st_cmp, c->st_down})
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (int i = 0; i < Ctx::kPipe; ++i) {
+        for (cudaEvent_t e : {c->ev_up[i], c->ev_cmp[i], c->ev_cnt[i], c->ev_down[i]}) if (e) cudaEventDestroy(e);
+        for (int j = 0; j < kSlotBufs; ++j) if (c->pslot[i].buf[j]) cudaFree(c->pslot[i].buf[j]);
+    }
     for (int i = 0; i < 2; ++i) {
-        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         if (c->slot[i].st) { cudaStreamSynchronize(c->slot[i].st); cudaStreamDestroy(c->slot[i].st); }
         for (int j = 0; j < kSlotBufs; ++j) if (c->slot[i].buf[j]) cudaFree(c->slot[i].buf[j]);
     }
@@ -305,7 +324,11 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
     }
     const int R = (int)p->resolution, W = (R + 31) / 32;
     const int64_t O = p->obstacles_num, oo = O + b->pomax;
-    const int64_t kSlice = io ? 1024 : 2048;
+    static const int64_t slice_env = getenv("PPNET_HOST_SLICE") ? atoll(getenv("PPNET_HOST_SLICE")) : 0;   // dev knob
+    // measured (10 k maps per call, two calls in flight): 1024 / 2048 / 4096 maps per slice -> 8.0 / 7.6 / 7.2 ms per call;
+    // a third of the call per slice keeps the three pipeline stages busy for smaller calls
+    const int64_t auto_slice = std::min<int64_t>(4096, std::max<int64_t>(1024, ((p->n_maps + 2) / 3 + 511) / 512 * 512));
+    const int64_t kSlice = slice_env > 0 ? slice_env : auto_slice;
     // per-map byte sizes of the outputs, slot buffer ids: 0 pathpt, 1 segpt, 2 obs, 3 bits, 4 small ints, 5 counters,
     // 6 segments f64, 7 segments f32, 8 / 9 / 10 verdict bytes, 11 verdict words x3 + lists + workspace
     const size_t b_pp = sizeof(double) * 2 * (size_t)b->np, b_sp = sizeof(double) * 2 * (size_t)b->nseg1;
@@ -322,17 +345,33 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
     }
     unsigned long long* cnt_keep = c->pinned_cnt;
     for (size_t i = 0; i < cnt_words; ++i) cnt_keep[i] = 0ull;
-    for (int i = 0; i < 2; ++i)
-        if (!c->ev[i]) PPNET_CUDA(cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming));
+    const bool want_small = p->out_angle || p->out_trans || p->out_obs_cnt || p->out_rand_cnt || p->out_tries || p->out_valid;
+    if (want_small && c->pinned_small_cap < b_small * (size_t)p->n_maps) {
+        if (c->pinned_small) cudaFreeHost(c->pinned_small);
+        c->pinned_small = nullptr; c->pinned_small_cap = 0;
+        const size_t want = b_small * (size_t)p->n_maps + b_small * (size_t)p->n_maps / 4 + 4096;
+        PPNET_CUDA(cudaHostAlloc((void**)&c->pinned_small, want, cudaHostAllocDefault));
+        c->pinned_small_cap = want;
+    }
+    constexpr int kPipe = Ctx::kPipe;
+    if (!c->st_up) {
+        PPNET_CUDA(cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
+        PPNET_CUDA(cudaStreamCreateWithFlags(&c->st_cmp, cudaStreamNonBlocking));
+        PPNET_CUDA(cudaStreamCreateWithFlags(&c->st_down, cudaStreamNonBlocking));
+        for (int i = 0; i < kPipe; ++i)
+            for (cudaEvent_t* e : {&c->ev_up[i], &c->ev_cmp[i], &c->ev_cnt[i], &c->ev_down[i]})
+                PPNET_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    cudaStream_t s_up = c->st_up, s_cmp = c->st_cmp, s_down = c->st_down;
     const bool need_bits = p->out_bits || anydda;
     const bool dev_words = one_array && (want_bits_out || want_free);
     int64_t free_total = 0, valid_total = 0;
 
     // second half of a slice: its index lists, once its counts have landed in the pinned staging area
     auto finish_lists = [&](int64_t k) -> int {
-        if (!want_free && !want_valid) return PPNET_OK;
-        Slot& s = c->slot[k & 1];
-        PPNET_CUDA(cudaEventSynchronize(c->ev[k & 1]));
+        if (!want_free && !want_valid) return PPNET_OK;                   // (ev_down was recorded right after the bulk copies)
+        Slot& s = c->pslot[k % kPipe];
+        PPNET_CUDA(cudaEventSynchronize(c->ev_cnt[k % kPipe]));
         const int64_t nm = std::min(kSlice, p->n_maps - k * kSlice), ns = nm * spm;
         const size_t words = (size_t)((ns + 31) / 32);
         char* wbase = (char*)s.buf[11];
@@ -340,7 +379,7 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
             const int64_t cnt = (int64_t)cnt_keep[8 * k + 4];
             const int32_t* d_idx = (const int32_t*)(wbase + 3 * 4 * words + 64);
             if (cnt > 0) {
-                PPNET_CUDA(cudaMemcpyAsync(io->free_idx + free_total, d_idx, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s.st));
+                PPNET_CUDA(cudaMemcpyAsync(io->free_idx + free_total, d_idx, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s_down));
                 c->d2h_bytes += 4 * cnt;
             }
             free_total += cnt;
@@ -349,17 +388,23 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
             const int64_t cnt = (int64_t)cnt_keep[8 * k + 5];
             const int32_t* d_idx = (const int32_t*)(wbase + 3 * 4 * words + 64 + (want_free ? 4 * (size_t)ns : 0));
             if (cnt > 0) {
-                PPNET_CUDA(cudaMemcpyAsync(io->valid_idx + valid_total, d_idx, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s.st));
+                PPNET_CUDA(cudaMemcpyAsync(io->valid_idx + valid_total, d_idx, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s_down));
                 c->d2h_bytes += 4 * cnt;
             }
             valid_total += cnt;
         }
+        PPNET_CUDA(cudaEventRecord(c->ev_down[k % kPipe], s_down));       // slot k % kPipe is free for slice k + kPipe
         return PPNET_OK;
     };
 
+    static const bool dbg = getenv("PPNET_HOST_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_lists = 0.0;
     int64_t k = 0;
     for (int64_t m0 = 0; m0 < p->n_maps; m0 += kSlice, ++k) {
-        Slot& s = c->slot[k & 1];
+        const int sb = (int)(k % kPipe);
+        Slot& s = c->pslot[sb];
         const int64_t nm = std::min(kSlice, p->n_maps - m0);
         const int64_t ns = nm * spm;
         const size_t words = (size_t)((ns + 31) / 32);
@@ -379,19 +424,24 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
             const size_t ws_elems = (size_t)ppnet_compact_bits_workspace_elems(ns);
             if ((rc = slot_reserve(s, 11, 3 * 4 * words + 64 + (want_free ? 4 * (size_t)ns : 0) + 4 * (size_t)nm + 64 + 8 * ws_elems)) != PPNET_OK)
                 return rc;
-            // the segment uploads go first: they overlap the previous slice's kernels and downloads
+            // uploads: back to back on the upload stream; the slot's segment buffers were last read by slice k - kPipe
+            if (k >= kPipe) PPNET_CUDA(cudaStreamWaitEvent(s_up, c->ev_cmp[sb], 0));
             if (io->segs_rc_f64) {
-                PPNET_CUDA(cudaMemcpyAsync(s.buf[6], io->segs_rc_f64 + 4 * m0 * spm, 32 * (size_t)ns, cudaMemcpyHostToDevice, s.st));
+                PPNET_CUDA(cudaMemcpyAsync(s.buf[6], io->segs_rc_f64 + 4 * m0 * spm, 32 * (size_t)ns, cudaMemcpyHostToDevice, s_up));
                 c->h2d_bytes += 32 * ns;
-            } else if (propose) {
-                if ((rc = ppnet_propose_segments(p->seed, (uint64_t)(p->map0 + m0), nm, spm, p->resolution, io->propose_sigma,
-                                                 (double*)s.buf[6], (void*)s.st)) != PPNET_OK) return rc;
             }
             if (io->segs_xy_f32) {
-                PPNET_CUDA(cudaMemcpyAsync(s.buf[7], io->segs_xy_f32 + 4 * m0 * spm, 16 * (size_t)ns, cudaMemcpyHostToDevice, s.st));
+                PPNET_CUDA(cudaMemcpyAsync(s.buf[7], io->segs_xy_f32 + 4 * m0 * spm, 16 * (size_t)ns, cudaMemcpyHostToDevice, s_up));
                 c->h2d_bytes += 16 * ns;
             }
+            PPNET_CUDA(cudaEventRecord(c->ev_up[sb], s_up));
         }
+        // kernels: wait for this slice's upload and for the download of the slice that used the slot's output buffers
+        if (io) PPNET_CUDA(cudaStreamWaitEvent(s_cmp, c->ev_up[sb], 0));
+        if (k >= kPipe) PPNET_CUDA(cudaStreamWaitEvent(s_cmp, c->ev_down[sb], 0));
+        if (propose &&
+            (rc = ppnet_propose_segments(p->seed, (uint64_t)(p->map0 + m0), nm, spm, p->resolution, io->propose_sigma,
+                                         (double*)s.buf[6], (void*)s_cmp)) != PPNET_OK) return rc;
         char* small = (char*)s.buf[4];
         double* d_angle = (double*)small;
         int32_t* d_trans = (int32_t*)(small + 8 * nm);
@@ -399,7 +449,7 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
         int32_t* d_rcnt = (int32_t*)(small + 20 * nm);
         int32_t* d_tries = (int32_t*)(small + 24 * nm);
         uint8_t* d_valid = (uint8_t*)(small + 28 * nm);
-        PPNET_CUDA(cudaMemsetAsync(s.buf[5], 0, 32, s.st));
+        PPNET_CUDA(cudaMemsetAsync(s.buf[5], 0, 32, s_cmp));
         ppnet_gen_params q = *p;
         q.bank_pathpt = b->pathpt; q.bank_segpt = b->segpt; q.bank_hull = b->hull; q.bank_hull_cnt = b->hull_cnt;
         q.bank_obs = b->obs; q.bank_obs_cnt = b->obs_cnt;
@@ -412,7 +462,7 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
         q.out_angle = d_angle; q.out_trans = d_trans; q.out_obs_cnt = d_ocnt; q.out_rand_cnt = d_rcnt;
         q.out_tries = d_tries; q.out_valid = d_valid;
         q.counters = (unsigned long long*)s.buf[5];
-        if ((rc = ppnet_generate_maps(&q, (void*)s.st)) != PPNET_OK) return rc;
+        if ((rc = ppnet_generate_maps(&q, (void*)s_cmp)) != PPNET_OK) return rc;
         char* wbase = io ? (char*)s.buf[11] : nullptr;
         uint32_t* w64 = (uint32_t*)wbase;
         uint32_t* w32 = (uint32_t*)(wbase + 4 * words);
@@ -428,56 +478,54 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
                                           io->clearance_px, io->bound, io->dot_mode, io->cmp_mode,
                                           io->verdict_f64 ? (uint8_t*)s.buf[8] : nullptr, io->verdict_f32 ? (uint8_t*)s.buf[9] : nullptr,
                                           (any64 && dev_words) ? w64 : nullptr, (any32 && dev_words) ? w32 : nullptr,
-                                          (void*)s.st)) != PPNET_OK) return rc;
+                                          (void*)s_cmp)) != PPNET_OK) return rc;
             if (anydda &&
                 (rc = ppnet_dda_gridcheck_rc64((const uint32_t*)s.buf[3], R, nm, (const double*)s.buf[6], ns, nullptr, spm,
                                                io->verdict_dda ? (uint8_t*)s.buf[10] : nullptr, nullptr, dev_words ? wdd : nullptr,
-                                               (void*)s.st)) != PPNET_OK) return rc;
+                                               (void*)s_cmp)) != PPNET_OK) return rc;
             if (want_free) {
                 const uint32_t* arr[3]; int na = 0;
                 if (any64) arr[na++] = w64;
                 if (any32) arr[na++] = w32;
                 if (anydda) arr[na++] = wdd;
                 if ((rc = ppnet_compact_bits(arr[0], na > 1 ? arr[1] : nullptr, na > 2 ? arr[2] : nullptr, ns, (int32_t)(m0 * spm), d_free,
-                                             d_counts, d_ws, (void*)s.st)) != PPNET_OK) return rc;
+                                             d_counts, d_ws, (void*)s_cmp)) != PPNET_OK) return rc;
             }
         } else if (io) {
             if (io->verdict_f64 &&
                 (rc = ppnet_segcheck_edage_f64((const double*)s.buf[6], ns, nullptr, spm, nm, (const double*)s.buf[2], d_ocnt,
                                                (int32_t)oo, io->clearance_px, io->bound, io->dot_mode, (uint8_t*)s.buf[8],
-                                               (void*)s.st)) != PPNET_OK) return rc;
+                                               (void*)s_cmp)) != PPNET_OK) return rc;
             if (io->verdict_f32 &&
                 (rc = ppnet_segcheck_mpnet_f32((const float*)s.buf[7], ns, nullptr, spm, nm, (const double*)s.buf[2], d_ocnt,
                                                (int32_t)oo, io->clearance_px, io->bound, (uint8_t*)s.buf[9], nullptr,
-                                               (void*)s.st)) != PPNET_OK) return rc;
+                                               (void*)s_cmp)) != PPNET_OK) return rc;
             if (io->verdict_dda &&
                 (rc = ppnet_dda_gridcheck((const uint32_t*)s.buf[3], R, nm, (const float*)s.buf[7], ns, nullptr, spm,
-                                          (uint8_t*)s.buf[10], nullptr, (void*)s.st)) != PPNET_OK) return rc;
+                                          (uint8_t*)s.buf[10], nullptr, (void*)s_cmp)) != PPNET_OK) return rc;
         }
         if (want_valid &&
-            (rc = ppnet_compact_u8_i32(d_valid, nm, 1, (int32_t)m0, d_vidx, d_counts + 1, (void*)s.st)) != PPNET_OK) return rc;
+            (rc = ppnet_compact_u8_i32(d_valid, nm, 1, (int32_t)m0, d_vidx, d_counts + 1, (void*)s_cmp)) != PPNET_OK) return rc;
 #define PPNET_D2H(host, devp, bytes)                                                                        \
     if (host) {                                                                                             \
-        PPNET_CUDA(cudaMemcpyAsync((char*)(host), devp, (bytes), cudaMemcpyDeviceToHost, s.st));            \
+        PPNET_CUDA(cudaMemcpyAsync((char*)(host), devp, (bytes), cudaMemcpyDeviceToHost, s_down));            \
         c->d2h_bytes += (int64_t)(bytes);                                                                   \
     }
+        PPNET_CUDA(cudaEventRecord(c->ev_cmp[sb], s_cmp));
+        PPNET_CUDA(cudaStreamWaitEvent(s_down, c->ev_cmp[sb], 0));
         if (want_free || want_valid) {          // the counts first: the host needs them to size the list copies
-            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 8 * k + 4, d_counts, 16, cudaMemcpyDeviceToHost, s.st));
+            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 8 * k + 4, d_counts, 16, cudaMemcpyDeviceToHost, s_down));
             c->d2h_bytes += 16;
         }
         if (p->counters)
-            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 8 * k, s.buf[5], 32, cudaMemcpyDeviceToHost, s.st));
-        PPNET_CUDA(cudaEventRecord(c->ev[k & 1], s.st));
+            PPNET_CUDA(cudaMemcpyAsync(cnt_keep + 8 * k, s.buf[5], 32, cudaMemcpyDeviceToHost, s_down));
+        PPNET_CUDA(cudaEventRecord(c->ev_cnt[sb], s_down));
         PPNET_D2H(p->out_pathpt ? (char*)p->out_pathpt + b_pp * m0 : nullptr, s.buf[0], b_pp * nm);
         PPNET_D2H(p->out_segpt ? (char*)p->out_segpt + b_sp * m0 : nullptr, s.buf[1], b_sp * nm);
         PPNET_D2H(p->out_obs ? (char*)p->out_obs + b_ob * m0 : nullptr, s.buf[2], b_ob * nm);
         PPNET_D2H(p->out_bits ? (char*)p->out_bits + b_bt * m0 : nullptr, s.buf[3], b_bt * nm);
-        PPNET_D2H(p->out_angle ? p->out_angle + m0 : nullptr, d_angle, 8 * (size_t)nm);
-        PPNET_D2H(p->out_trans ? p->out_trans + 2 * m0 : nullptr, d_trans, 8 * (size_t)nm);
-        PPNET_D2H(p->out_obs_cnt ? p->out_obs_cnt + m0 : nullptr, d_ocnt, 4 * (size_t)nm);
-        PPNET_D2H(p->out_rand_cnt ? p->out_rand_cnt + m0 : nullptr, d_rcnt, 4 * (size_t)nm);
-        PPNET_D2H(p->out_tries ? p->out_tries + m0 : nullptr, d_tries, 4 * (size_t)nm);
-        PPNET_D2H(p->out_valid ? p->out_valid + m0 : nullptr, d_valid, (size_t)nm);
+        // angle | trans | obs_cnt | rand_cnt | tries | valid of this slice: ONE copy into pinned staging, scattered below
+        PPNET_D2H(want_small ? c->pinned_small + b_small * (size_t)m0 : nullptr, small, 29 * (size_t)nm);
         if (io) {
             PPNET_D2H(io->verdict_f64 ? io->verdict_f64 + m0 * spm : nullptr, s.buf[8], (size_t)ns);
             PPNET_D2H(io->verdict_f32 ? io->verdict_f32 + m0 * spm : nullptr, s.buf[9], (size_t)ns);
@@ -488,14 +536,33 @@ static int generate_host_run(Ctx* c, Bank* b, const ppnet_gen_params* p, const p
             PPNET_D2H(io->vbits_dda ? io->vbits_dda + (m0 * spm) / 32 : nullptr, wdd, 4 * words);
             PPNET_D2H(io->out_segs_rc ? io->out_segs_rc + 4 * m0 * spm : nullptr, s.buf[6], 32 * (size_t)ns);
         }
+        if (!want_free && !want_valid) PPNET_CUDA(cudaEventRecord(c->ev_down[sb], s_down));
+        const double tl = now();
         if (k > 0 && (rc = finish_lists(k - 1)) != PPNET_OK) return rc;
+        t_lists += now() - tl;
     }
+    const double t_issued = now();
     if (k > 0) { int rc = finish_lists(k - 1); if (rc != PPNET_OK) return rc; }
-    PPNET_CUDA(cudaStreamSynchronize(c->slot[0].st));
-    PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
+    PPNET_CUDA(cudaStreamSynchronize(s_down));                           // every slice ends on the download stream
+    PPNET_CUDA(cudaStreamSynchronize(s_cmp));
+    PPNET_CUDA(cudaStreamSynchronize(s_up));
+    if (dbg)
+        fprintf(stderr, "[ppnet host] %lld slices: issue %.2f ms (of which waiting for list counts %.2f), final sync %.2f ms\n",
+                (long long)k, t_issued - t_begin, t_lists, now() - t_issued);
     if (p->counters)
         for (int64_t q = 0; q < n_slices; ++q)
             for (int i = 0; i < 4; ++i) p->counters[i] += cnt_keep[8 * q + i];
+    if (want_small)
+        for (int64_t m0 = 0; m0 < p->n_maps; m0 += kSlice) {
+            const size_t nm = (size_t)std::min(kSlice, p->n_maps - m0);
+            const char* blk = c->pinned_small + b_small * (size_t)m0;
+            if (p->out_angle) memcpy(p->out_angle + m0, blk, 8 * nm);
+            if (p->out_trans) memcpy(p->out_trans + 2 * m0, blk + 8 * nm, 8 * nm);
+            if (p->out_obs_cnt) memcpy(p->out_obs_cnt + m0, blk + 16 * nm, 4 * nm);
+            if (p->out_rand_cnt) memcpy(p->out_rand_cnt + m0, blk + 20 * nm, 4 * nm);
+            if (p->out_tries) memcpy(p->out_tries + m0, blk + 24 * nm, 4 * nm);
+            if (p->out_valid) memcpy(p->out_valid + m0, blk + 28 * nm, nm);
+        }
     if (want_free) *io->free_count = free_total;
     if (want_valid) *io->valid_count = valid_total;
     return PPNET_OK;
@@ -510,8 +577,8 @@ static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const 
     if (rc != PPNET_OK) {
         // copies into the caller's buffers may still be in flight on both streams: let them land before the caller
         // sees the error (and possibly frees those buffers)
-        cudaStreamSynchronize(c->slot[0].st);
-        cudaStreamSynchronize(c->slot[1].st);
+        for (cudaStream_t st : {c->st_up, c->st_cmp, c->st_down})
+            if (st) cudaStreamSynchronize(st);
         cudaGetLastError();
     }
     return rc;

@@ -413,7 +413,7 @@ isle_kernel(ppnet_path_params P) {
     const double2* hull = reinterpret_cast<const double2*>(P.hull) + p * P.hmax;
     const double step_len = __dmul_rn(__ddiv_rn(1.0, P.resolution), P.map_size);
     const double long_edge = __ddiv_rn(5.0, step_len);
-    const double thr = (double)(int)rint(__dmul_rn(__ddiv_rn(P.clearance, step_len), 0.2));   // int(np.round(c/step*0.2))
+    const double thr = (double)(int)rint(__dmul_rn(__ddiv_rn(P.clearance, step_len), P.width_coef));   // int(np.round(c/step*width_coef))
     const bool straight_path = P.path_straight[p] != 0;   // path_obstacles(): a straight Path gets no isles (:149-150)
     for (int i = warp; i < H; i += kIsleThreads / 32) {
         const int j = (i == H - 1) ? 0 : i + 1;
@@ -582,6 +582,7 @@ obstacles_kernel(ppnet_path_params P) {
         }
     }
     if (lane == 0) {
+        if (P.hull_cnt[p] > P.hmax || P.isle_cnt[p] > P.hmax) status |= 8;   // hull / isle capacity overflow: unusable bank entry
         P.obs_cnt[p] = min(n_obs, P.pomax);
         P.obst_rand_used[p] = used;
         P.status[p] = status;

@@ -18,6 +18,8 @@
 //     of shared-memory atomics; "owner already hit" is a register test.
 //   * "exact only" circles / segments are encoded in the data (margin = +inf / L = NaN fall through every filter
 //     comparison into `edge_exact`), no flag words in the pair loop.
+#include <cstdlib>
+
 #include "segcheck.cuh"
 
 namespace ppnet {
@@ -49,8 +51,11 @@ __device__ __forceinline__ bool flavour_pair(T s0, T s1, T e0, T e1, T L, T es, 
 }
 
 template <typename TIN> struct VOcc;
+#ifndef PPNET_VPREFETCH
+#define PPNET_VPREFETCH 1
+#endif
 #ifndef PPNET_VOCC
-#define PPNET_VOCC 5
+#define PPNET_VOCC 6
 #endif
 template <> struct VOcc<double> { static constexpr int kMinBlocks = PPNET_VOCC; };
 template <> struct VOcc<float> { static constexpr int kMinBlocks = 7; };
@@ -97,7 +102,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
     __shared__ float2 c_em[kCircTile];            // (eps64 * mc, eps32 * mc), +inf = exact only
     __shared__ uint4 edge_lo[2][kBins], edge_hi[2][kBins];
     __shared__ uint4 LT[2][kBins], GT[2][kBins];
-    __shared__ uint32_t live_mask[4], odd_mask[4];
+    __shared__ __align__(16) uint32_t live_mask[4], odd_mask[4];
     // per-warp slots, SoA: what a pair needs of its segment
     __shared__ TIN sl_s0[kVWarps][32], sl_s1[kVWarps][32], sl_e0[kVWarps][32], sl_e1[kVWarps][32];
     __shared__ float2 sl_a[kVWarps][32];          // (L, es) of the float64 flavour, as floats (NaN L = verbatim)
@@ -109,9 +114,16 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
     const float bscale = use_grid ? (float)kBins / (float)bound : 0.0f;
     const double* __restrict__ mobs = obs + (size_t)m * omax * 3;
 
-    int64_t i = base + 32 * warp + lane;
+    // CTA-relative 32-bit indices from here on (chunk <= 8192)
+    const int n_here = (int)(end - base);
+    pts += 4 * base;
+    if (v64) v64 += base;
+    if (v32) v32 += base;
+    int i = 32 * warp + lane;
     TIN a0 = TIN(0), a1 = TIN(0), b0 = TIN(0), b1 = TIN(0);
-    if (i < end) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1);
+#if PPNET_VPREFETCH
+    if (i < n_here) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1);
+#endif
 
     for (int t0 = 0; t0 == 0 || t0 < cnt; t0 += kCircTile) {
         const int nt = max(0, min(kCircTile, cnt - t0));
@@ -172,13 +184,18 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             }
         }
         __syncthreads();
-        const uint32_t lv0 = live_mask[0], lv1 = live_mask[1], lv2 = live_mask[2], lv3 = live_mask[3];
-        const uint32_t od0 = odd_mask[0], od1 = odd_mask[1], od2 = odd_mask[2], od3 = odd_mask[3];
-        if (!first_tile) { i = base + 32 * warp + lane; if (i < end) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1); }
+#if PPNET_VPREFETCH
+        if (!first_tile) { i = 32 * warp + lane; if (i < n_here) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1); }
+#else
+        i = 32 * warp + lane;
+#endif
 
-        for (int64_t batch = base + 32 * warp; batch < end; batch += kVThreads) {
-            const bool have = i < end;
-            const int64_t cur = i;
+        for (int batch = 32 * warp; batch < n_here; batch += kVThreads) {
+            const bool have = i < n_here;
+            const int cur = i;
+#if !PPNET_VPREFETCH
+            if (have) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1);
+#endif
             // ---- per-segment setup (both flavours), then the next batch's load goes out
             bool oob64 = false, oob32 = false, verb64 = false, verb32 = false;
             TIN s0, s1, e0, e1;                                   // (x, y) of the input precision
@@ -211,20 +228,23 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                 es32 = Filt<float>::eps * ms;
             }
             i += kVThreads;
-            if (i < end) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1);
+#if PPNET_VPREFETCH
+            if (i < n_here) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1);     // next batch's load overlaps this one's work
+#endif
             // state of this segment so far (later circle tiles continue from the stored verdict)
             bool hit64 = oob64, hit32 = oob32;
             if (!first_tile) {
                 uint32_t p64 = 0u, p32 = 0u;
-                if (DO64) p64 = v64 ? (have && v64[cur] != 0) : ((vbits_load(b64, n_words, batch) >> lane) & 1u);
-                if (DO32) p32 = v32 ? (have && v32[cur] != 0) : ((vbits_load(b32, n_words, batch) >> lane) & 1u);
+                if (DO64) p64 = v64 ? (have && v64[cur] != 0) : ((vbits_load(b64, n_words, base + batch) >> lane) & 1u);
+                if (DO32) p32 = v32 ? (have && v32[cur] != 0) : ((vbits_load(b32, n_words, base + batch) >> lane) & 1u);
                 hit64 = p64 != 0u; hit32 = p32 != 0u;
             }
             const bool open = have && ((DO64 && !hit64) || (DO32 && !hit32));
             uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
             if (open && nt > 0) {
+                const uint4 lv = *reinterpret_cast<const uint4*>(live_mask);     // broadcast reads
                 if (verb64 || verb32 || !use_grid) {
-                    c0 = lv0; c1 = lv1; c2 = lv2; c3 = lv3;
+                    c0 = lv.x; c1 = lv.y; c2 = lv.z; c3 = lv.w;
                 } else {
                     // one query for both flavours: pieces <= 3 bins long, each box inflated by the float32 margin, the
                     // float32 rounding of the endpoints (<= 2^-24 |coord|) and float slop
@@ -243,7 +263,8 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                         n0 &= p.x | r.x | u.x | v.x; n1 &= p.y | r.y | u.y | v.y;
                         n2 &= p.z | r.z | u.z | v.z; n3 &= p.w | r.w | u.w | v.w;
                     }
-                    c0 = lv0 & (~n0 | od0); c1 = lv1 & (~n1 | od1); c2 = lv2 & (~n2 | od2); c3 = lv3 & (~n3 | od3);
+                    const uint4 od = *reinterpret_cast<const uint4*>(odd_mask);
+                    c0 = lv.x & (~n0 | od.x); c1 = lv.y & (~n1 | od.y); c2 = lv.z & (~n2 | od.z); c3 = lv.w & (~n3 | od.w);
                 }
             }
             sl_s0[warp][lane] = s0; sl_s1[warp][lane] = s1; sl_e0[warp][lane] = e0; sl_e1[warp][lane] = e1;
@@ -319,12 +340,12 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             if (DO64) {                                            // hm64 started from the bounds test / stored verdict
                 const bool h = (hm64 >> lane) & 1u;
                 if (v64 && have && (first_tile || h)) v64[cur] = h ? 1 : 0;
-                if (b64 && lane == 0) vbits_or(b64, batch, hm64 & valid, exclusive_words != 0, first_tile);
+                if (b64 && lane == 0) vbits_or(b64, base + batch, hm64 & valid, exclusive_words != 0, first_tile);
             }
             if (DO32) {
                 const bool h = (hm32 >> lane) & 1u;
                 if (v32 && have && (first_tile || h)) v32[cur] = h ? 1 : 0;
-                if (b32 && lane == 0) vbits_or(b32, batch, hm32 & valid, exclusive_words != 0, first_tile);
+                if (b32 && lane == 0) vbits_or(b32, base + batch, hm32 & valid, exclusive_words != 0, first_tile);
             }
             __syncwarp();
         }
@@ -354,12 +375,17 @@ static int launch_verdict(const TIN* pts, int64_t n_segs, const int64_t* seg_off
         if (b32) PPNET_CUDA(cudaMemsetAsync(b32, 0, 4 * (size_t)n_words, st));
     }
     dim3 grid((unsigned)n_maps, (unsigned)chunks);
+    static const int pad = getenv("PPNET_VERDICT_PAD") ? atoi(getenv("PPNET_VERDICT_PAD")) : 0;   // dev knob: caps resident CTAs
+    if (pad > 0) {
+        cudaFuncSetAttribute(verdict_kernel<PPNET_DOT_UNFUSED, DO64, DO32, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+        cudaFuncSetAttribute(verdict_kernel<PPNET_DOT_FUSED_SKX, DO64, DO32, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    }
     if (dot_mode == PPNET_DOT_UNFUSED)
-        verdict_kernel<PPNET_DOT_UNFUSED, DO64, DO32, TIN><<<grid, kVThreads, 0, st>>>(
+        verdict_kernel<PPNET_DOT_UNFUSED, DO64, DO32, TIN><<<grid, kVThreads, pad, st>>>(
             pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (TIN)bound, cmp_mode, v64, v32, b64, b32,
             exclusive, n_words);
     else
-        verdict_kernel<PPNET_DOT_FUSED_SKX, DO64, DO32, TIN><<<grid, kVThreads, 0, st>>>(
+        verdict_kernel<PPNET_DOT_FUSED_SKX, DO64, DO32, TIN><<<grid, kVThreads, pad, st>>>(
             pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (TIN)bound, cmp_mode, v64, v32, b64, b32,
             exclusive, n_words);
     PPNET_LAUNCH_CHECK("verdict_kernel");

@@ -76,12 +76,12 @@ class Path:
         self._id = None
         self._polys = None
         self._b = None            # host copies of the last PathBatch
-        self._key = None          # (resolution, map_size) it was computed for
+        self._key = None          # (resolution, map_size, width_coef) it was computed for
 
     # ------------------------------------------------------------------ device work
-    def _run(self, resolution=224, map_size=50, batch=None, index=0):
+    def _run(self, resolution=224, map_size=50, batch=None, index=0, width_coef=0.2):
         """(Re)compute everything for this path at the given raster; `batch`/`index` adopt a row of a PathGroup launch."""
-        key = (int(resolution), float(map_size))
+        key = (int(resolution), float(map_size), float(width_coef))
         if batch is None:
             if self._b is not None and self._key == key:
                 return self._b
@@ -98,9 +98,9 @@ class Path:
                 kw["force_straight"] = torch.ones([1], dtype=torch.uint8, device=self.device)
             else:
                 kw.setdefault("force_straight", torch.zeros([1], dtype=torch.uint8, device=self.device))
-            out = ops.path_synthesize(self._id, 1, seg_num=self.SegNum, poly_order=self.PolyOrder, clearance=self.Clearance,
-                                      map_size=map_size, resolution=resolution, seed=_state.current_seed(), want_space=True,
-                                      device=self.device, **kw)
+            out = ops.path_synthesize_checked(self._id, 1, seg_num=self.SegNum, poly_order=self.PolyOrder, clearance=self.Clearance,
+                                              map_size=map_size, resolution=resolution, seed=_state.current_seed(), want_space=True,
+                                              device=self.device, width_coef=width_coef, **kw)
             self._b = {k: v.cpu().numpy()[0] for k, v in vars(out).items() if isinstance(v, torch.Tensor)}
         else:
             self._b = {k: v[index] for k, v in batch.items()}
@@ -144,6 +144,10 @@ class Path:
         return bool(ok.item()), out[0].cpu().numpy()
 
     def path_space(self, resolution=224, map_size=50, map_offset=112):
+        # the reference only ever calls this with map_offset = resolution / 2 (PathGenerate.py:29; the default 112 = 224 / 2):
+        # boundary_check (Path.py:100-111) centres its rotation there, and so do the kernels
+        if float(map_offset) != float(resolution) / 2:
+            raise ops.PPNetError("path_space: map_offset must be resolution / 2 (got %r for resolution %r)" % (map_offset, resolution))
         self.Resolution, self.MapSize, self.MapOffset = resolution, map_size, map_offset
         b = self._run(resolution, map_size)
         H = int(b["hull_cnt"])
@@ -193,9 +197,28 @@ class Path:
         return space
 
     def search_isle(self, width_coef=0.2):
+        """Path.py:502-537.  A width_coef other than the cached launch's recomputes this path (same Philox draws, so the
+        geometry is unchanged; only the isle depth threshold int(round(c / step * width_coef)) moves)."""
+        if self._b is None or self._key is None:
+            raise ops.PPNetError("search_isle: call path_space / path_obstacles first (it needs Resolution, MapSize and the hull)")
+        if float(width_coef) != self._key[2]:
+            if self._id is None:
+                raise ops.PPNetError("search_isle: this Path was adopted from a batch without an id; cannot recompute")
+            self._b = None
+            self._run(self._key[0], self._key[1], width_coef=width_coef)
         b = self._b
         return [self.PathPoint[lo:hi] for lo, hi in b["isle"][:int(b["isle_cnt"])]]
 
     def set_obstacles(self, boundarys):
+        """Path.py:463-500 on the isles search_isle returned (the reference's only call, Path.py:151-152).  The kernel
+        places the obstacles of exactly those isles; other boundary lists are refused rather than silently ignored."""
         b = self._b
+        if b is None:
+            raise ops.PPNetError("set_obstacles: call path_space / path_obstacles first")
+        isles = [self.PathPoint[lo:hi] for lo, hi in b["isle"][:int(b["isle_cnt"])]]
+        given = list(boundarys)
+        same = len(given) == len(isles) and all(np.shape(g) == np.shape(i) and np.array_equal(np.asarray(g), np.asarray(i))
+                                                for g, i in zip(given, isles))
+        if not same:
+            raise ops.PPNetError("set_obstacles: only the isles returned by search_isle() of this path are supported")
         return [[float(o[0]), float(o[1]), float(o[2])] for o in b["obs"][:int(b["obs_cnt"])]]

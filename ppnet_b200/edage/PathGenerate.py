@@ -31,9 +31,11 @@ class PathGroup:
         # the reference loops until path_num paths are accepted; path_obstacles() always accepts (Path.py:174 tests a
         # tuple), so exactly path_num paths are drawn.  The 1 % forced-straight draw is part of each path's stream.
         first = _state.next_path_ids(self.PathNum)
-        out = ops.path_synthesize(first, self.PathNum, seg_num=path_seg_num, poly_order=poly_order, clearance=clearance,
-                                  map_size=self.MapSize, resolution=self.Resolution, seed=_state.current_seed(),
-                                  want_space=True, device=self.device)
+        # capacities / iteration guards are checked (and grown) here: a truncated hull would let boundary_check accept
+        # placements that leave the image
+        out = ops.path_synthesize_checked(first, self.PathNum, seg_num=path_seg_num, poly_order=poly_order, clearance=clearance,
+                                          map_size=self.MapSize, resolution=self.Resolution, seed=_state.current_seed(),
+                                          want_space=True, device=self.device)
         self.batch = out
         self.bank = out.to_bank()
         host = {k: v.cpu().numpy() for k, v in vars(out).items() if isinstance(v, torch.Tensor)}

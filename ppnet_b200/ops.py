@@ -418,6 +418,7 @@ _PATH_FIELDS = [
     ("seg_num", ctypes.c_int32), ("poly_order", ctypes.c_int32), ("hmax", ctypes.c_int32), ("pomax", ctypes.c_int32),
     ("max_obst_iter", ctypes.c_int32), ("max_obst_rand", ctypes.c_int32),
     ("clearance", ctypes.c_double), ("map_size", ctypes.c_double), ("resolution", ctypes.c_double),
+    ("width_coef", ctypes.c_double),
     ("seed", ctypes.c_uint64),
 ]
 _PATH_INPUTS = ["force_straight", "in_straight", "in_y", "in_uend", "in_poly", "in_obst_rand", "in_obst_rand_cnt", "in_hull",
@@ -483,7 +484,7 @@ class PathBatch:
 
 
 def path_synthesize(path0, n_paths, seg_num=10, poly_order=4, clearance=1.0, map_size=50.0, resolution=224,
-                    seed=DEFAULT_SEED, hmax=64, pomax=32, max_obst_iter=256, want_space=False, device="cuda",
+                    seed=DEFAULT_SEED, hmax=64, pomax=32, max_obst_iter=256, want_space=False, device="cuda", width_coef=0.2,
                     force_straight=None, in_straight=None, in_y=None, in_uend=None, in_poly=None, in_obst_rand=None,
                     in_obst_rand_cnt=None, in_hull=None, in_hull_cnt=None):
     """PathGroup.generate's per-path work for global path ids [path0, path0 + n_paths)
@@ -498,6 +499,7 @@ def path_synthesize(path0, n_paths, seg_num=10, poly_order=4, clearance=1.0, map
     p.path0, p.n_paths, p.seg_num, p.poly_order, p.hmax, p.pomax = path0, n_paths, S, int(poly_order), hmax, pomax
     p.max_obst_iter, p.clearance, p.map_size, p.resolution = max_obst_iter, float(clearance), float(map_size), float(R)
     p.seed = seed
+    p.width_coef = float(width_coef)
     ins = dict(force_straight=(force_straight, torch.uint8), in_straight=(in_straight, torch.uint8),
                in_y=(in_y, torch.float64), in_uend=(in_uend, torch.float64), in_poly=(in_poly, torch.float64),
                in_obst_rand=(in_obst_rand, torch.float32), in_obst_rand_cnt=(in_obst_rand_cnt, torch.int32),
@@ -519,6 +521,41 @@ def path_synthesize(path0, n_paths, seg_num=10, poly_order=4, clearance=1.0, map
     check(lib().ppnet_path_synthesize(ctypes.byref(p), _stream()), "ppnet_path_synthesize")
     out.n_paths, out.path0 = n_paths, path0
     return out
+
+
+PATH_STATUS_BITS = {1: "max_obst_iter reached in set_obstacles", 2: "supplied torch.rand draws exhausted",
+                    4: "path-obstacle capacity (pomax) overflow", 8: "hull / isle capacity (hmax) overflow"}
+
+
+def path_synthesize_checked(path0, n_paths, hmax=64, pomax=32, max_obst_iter=256, **kw):
+    """path_synthesize, then the guards the kernels report instead of acting on (`status`, `hull_cnt`): on a capacity
+    overflow or an exhausted iteration guard the launch is repeated with larger capacities (draws are keyed by the path
+    id, so the repeat reproduces every path that was fine); what still fails raises.  The reference has no capacities --
+    its lists grow and its set_obstacles loops until it succeeds (EDaGe-PP/Path.py:463-500)."""
+    while True:
+        out = path_synthesize(path0, n_paths, hmax=hmax, pomax=pomax, max_obst_iter=max_obst_iter, **kw)
+        st = int(torch.bitwise_or(out.status.max(), 0).item()) if n_paths else 0
+        bits = 0
+        if n_paths:
+            for b in (1, 2, 4, 8):
+                if bool((out.status & b).any().item()):
+                    bits |= b
+            if int(out.hull_cnt.max().item()) > hmax:
+                bits |= 8
+        if bits == 0:
+            return out
+        if bits & 2:
+            raise PPNetError("path_synthesize: %s" % PATH_STATUS_BITS[2])
+        grown = False
+        if bits & 8 and hmax < 128:
+            hmax, grown = 128, True
+        if bits & 4 and pomax < 512:
+            pomax, grown = pomax * 2, True
+        if bits & 1 and max_obst_iter < (1 << 16):
+            max_obst_iter, grown = max_obst_iter * 8, True
+        if not grown:
+            raise PPNetError("path_synthesize: " + "; ".join(v for k, v in PATH_STATUS_BITS.items() if bits & k) +
+                             " (status %d) at the largest supported capacities" % st)
 
 
 def bits_to_image(bits, resolution, add=None):
@@ -659,3 +696,43 @@ def compact_bits(a, b=None, c=None, n=None, out=None, idx_base=0):
                                _ptr(ws), _stream()),
           "ppnet_compact_bits")
     return idx, cnt, ws
+
+
+def digest(t, unit0, acc, rows=None, row_elems=0, salt=0):
+    """*acc += 64-bit content digest of the per-unit (per-map) array `t` [n_units, ...] (ppnet_digest_u32): additive over any
+    split of the global unit range, so N ranks digesting their shards and summing (mod 2^64) must reproduce the digest of one
+    rank doing everything.  `acc` int64[1] device tensor; `rows` int32[n_units] limits unit u to its first rows[u] rows of
+    `row_elems` elements."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or not t.is_contiguous():
+        raise PPNetError("digest: needs a contiguous CUDA tensor")
+    _need(acc, torch.int64, "acc")
+    n = t.shape[0]
+    if n == 0:
+        return acc
+    bytes_per_unit = t.numel() // n * t.element_size()
+    if bytes_per_unit % 4:
+        raise PPNetError("digest: bytes per unit must be a multiple of 4")
+    if rows is not None:
+        _need(rows, torch.int32, "rows")
+    check(lib().ppnet_digest_u32(_ptr(t), ctypes.c_int64(bytes_per_unit // 4), ctypes.c_int64(n), ctypes.c_uint64(unit0), _ptr(rows),
+                                 ctypes.c_int32(row_elems * t.element_size() // 4), ctypes.c_uint64(salt), _ptr(acc), _stream()),
+          "ppnet_digest_u32")
+    return acc
+
+
+def digest_maps(gen, acc):
+    """Digest of everything one generate_maps launch produced for maps [gen.map0, gen.map0 + gen.n_maps): labels
+    (angle, translation, SegPoint, PathPoint), the accepted obstacle sets (obs_cnt rows) and the bit-packed maps."""
+    g0 = gen.map0
+    digest(gen.angle, g0, acc, salt=1)
+    digest(gen.trans, g0, acc, salt=2)
+    if gen.segpt is not None:
+        digest(gen.segpt, g0, acc, salt=3)
+    if gen.pathpt is not None:
+        digest(gen.pathpt, g0, acc, salt=4)
+    digest(gen.obs, g0, acc, rows=gen.obs_cnt, row_elems=3, salt=5)
+    digest(gen.obs_cnt, g0, acc, salt=6)
+    if gen.bits is not None:
+        digest(gen.bits, g0, acc, salt=7)
+    digest(gen.valid.view(torch.uint8).to(torch.int32), g0, acc, salt=8)
+    return acc
