@@ -790,6 +790,43 @@ def run_ours(args):
                            "pinned host buffers",
                     "cpu_affinity": numa})
         e2e_gen, _, _ = e2e_run(checks_gen, 40_000)
+
+        # the ceiling of this box for these bytes: raw pinned copies of the same volume per pass, both directions at once,
+        # every rank at the same time (no kernels, no API of ours) -- at N > 1 the ranks share the host's memory system
+        def raw_copy_ms(up_bytes, down_bytes, reps=3, chunk=32 << 20):
+            hi = torch.empty(max(up_bytes, 1), dtype=torch.uint8).pin_memory()
+            ho = torch.empty(max(down_bytes, 1), dtype=torch.uint8).pin_memory()
+            di = torch.empty(max(up_bytes, 1), dtype=torch.uint8, device=dev)
+            do = torch.empty(max(down_bytes, 1), dtype=torch.uint8, device=dev)
+            su, sd = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+            def once():
+                for o in range(0, max(up_bytes, down_bytes), chunk):
+                    if o < up_bytes:
+                        with torch.cuda.stream(su):
+                            di[o:o + chunk].copy_(hi[o:o + chunk], non_blocking=True)
+                    if o < down_bytes:
+                        with torch.cuda.stream(sd):
+                            ho[o:o + chunk].copy_(do[o:o + chunk], non_blocking=True)
+            once()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                once()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return 1e3 * dt
+
+        for e in (e2e, e2e_gen):
+            raw = raw_copy_ms(int(e["h2d_bytes_per_pass"]), int(e["d2h_bytes_per_pass"]))
+            e["raw_copy_ms_per_pass"] = raw
+            e["frac_of_raw_copy_ceiling"] = raw / e["ms_per_pass"]
+            e["raw_copy_note"] = ("raw pinned cudaMemcpyAsync of the same bytes per pass, both directions at once on every rank "
+                                  "simultaneously: what this box's PCIe + host memory system delivers at this N")
         e2e_gen["api"] = ("same call with the device-side segment source (propose_sigma): generator-mode callers upload nothing; "
                           "not the contract's e2e (no host->device input copy), reported beside it")
 
