@@ -44,6 +44,16 @@ void count_launch(int n = 1);
 
 constexpr int kNumSMs = 148;   // B200
 
+// Bounds / protocol checks of our own on every shared-memory queue, stage and scatter index (compute-sanitizer is not
+// available on the GPU pool): compiled in by `make debug` (-DPPNET_DEBUG_BOUNDS -> libppnet_b200_dbg.so), the GPU
+// parity tests are then run against that library (scripts/gpu_debug_bounds.sh); compiled out of the product.
+#ifdef PPNET_DEBUG_BOUNDS
+#include <cassert>
+#define PPNET_ASSERT(cond) assert(cond)
+#else
+#define PPNET_ASSERT(cond) ((void)0)
+#endif
+
 // ---- the reference's 2-vector dot product (np.dot -> OpenBLAS ddot), see SURVEY 8(c) ----------
 template <int MODE>
 __device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) {

@@ -155,6 +155,7 @@ compact_bits_scatter_kernel(const uint32_t* __restrict__ a, const uint32_t* __re
         const uint32_t vk = __shfl_sync(0xffffffffu, v, k);
         if (vk == 0u) continue;
         const int ek = __shfl_sync(0xffffffffu, excl, k);
+        PPNET_ASSERT(!((vk >> lane) & 1u) || off + ek + __popc(vk & ((1u << lane) - 1u)) < n);
         if ((vk >> lane) & 1u)
             out_idx[off + ek + __popc(vk & ((1u << lane) - 1u))] = idx_base + (int32_t)(((w - lane + k) << 5) + lane);
     }
@@ -178,6 +179,7 @@ compact_u8_onecta_kernel(const uint8_t* __restrict__ flags, int64_t n, uint8_t k
         int before = 0, tile = 0;
         for (int w = 0; w < 32; ++w) { const int c = wcnt[w]; before += w < warp ? c : 0; tile += c; }
         const int64_t carry = carry_s;
+        PPNET_ASSERT(!mine || carry + before + __popc(bal & ((1u << lane) - 1u)) < n);
         if (mine) out_idx[carry + before + __popc(bal & ((1u << lane) - 1u))] = idx_base + (int32_t)i;
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + tile;

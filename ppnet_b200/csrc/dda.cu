@@ -158,6 +158,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
                 const int dm = xmaj ? dy : dx;                             // minor-axis delta, |dm| <= n
                 const unsigned flags = (xmaj ? 1u : 0u) | (dM > 0 ? 2u : 0u) | (kM - 1 < n ? 4u : 0u) | (dm < 0 ? 8u : 0u);
                 const int pos = wb + __popc(wm & lt);
+                PPNET_ASSERT(pos >= 0 && pos < kDdaStage && a >= 0 && a < R * RS);
                 stage[pos] = make_int4((int)((unsigned)a | (flags << 28)), kend | ((xmaj ? y0 : x0) << 16), 2 * abs(dm), 2 * n);
                 sidx[pos] = (uint16_t)t;
             }
@@ -188,6 +189,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
                 if (!exhausted) {
                     const int my = wnext + __popc(need & lt);
                     if (!live && my < wend) {
+                        PPNET_ASSERT(my >= 0 && my < np_ && sidx[my] < ns);
                         const int4 q = stage[my];
                         res_ptr = res + sidx[my];
                         const unsigned flags = (unsigned)q.x >> 28;
@@ -217,6 +219,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
             for (int u = 0; u < 4; ++u) {                                  // 4 cells between two warp votes; straight-line code
                 const bool in = live && (unsigned)cm < (unsigned)R;       // minor coordinate still inside?
                 uint32_t word = 0xffffffffu;
+                PPNET_ASSERT(!in || (a >= 0 && (a >> 5) < R * W));
                 if (in) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(bm_s + ((uint32_t)(a >> 5) << 2)));
                 const bool blocked = (word >> (a & 31)) & 1u;              // occupied, or outside by the minor axis
                 const bool done = live && (blocked || k == kend);

@@ -344,6 +344,7 @@ generate_kernel(ppnet_gen_params P) {
         __syncthreads();
         // (disk, row) tasks flattened over the CTA: every thread gets the same number of row spans whatever the radii
         const int n_disk = O + n_po;
+        PPNET_ASSERT(n_disk <= omax_out);
         for (int k = threadIdx.x; k < n_disk; k += kGenThreads) {
             int i0 = 0, i1 = 0;
             if (k >= O || acc_s[k])                        // rejected candidates paint nothing
@@ -378,6 +379,7 @@ generate_kernel(ppnet_gen_params P) {
             while (hi - k > 1) { const int mid = (k + hi) >> 1; if (task_s[mid] <= t_lo) k = mid; else hi = mid; }
             for (int t = t_lo; t < t_hi; ++t) {
                 while (t >= task_s[k + 1]) ++k;
+                PPNET_ASSERT(k < n_disk && row0_s[k] + (t - task_s[k]) >= 0 && row0_s[k] + (t - task_s[k]) < (int)R);
                 raster_disk_row(bm, (int)R, W, sobs[3 * k], sobs[3 * k + 1], __dadd_rn(sobs[3 * k + 2], P.raster_inflate),
                                 row0_s[k] + (t - task_s[k]));
             }

@@ -72,6 +72,7 @@ __device__ __forceinline__ void vbits_or(uint32_t* w, int64_t i0, uint32_t m, bo
     const int64_t k = i0 >> 5;
     const int sh = (int)(i0 & 31);
     if (exclusive) {                                         // this warp owns the whole word
+        PPNET_ASSERT(sh == 0);
         if (first) w[k] = m;
         else if (m) w[k] |= m;
         return;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(kVThreads, VOcc<TIN>::kMinBlocks)
 verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
                const double* __restrict__ obs, const int32_t* __restrict__ obs_cnt, int omax, double clearance,
                TIN bound, int cmp64, uint8_t* __restrict__ v64, uint8_t* __restrict__ v32, uint32_t* __restrict__ b64,
-               uint32_t* __restrict__ b32, int exclusive_words, int64_t n_words) {
+               uint32_t* __restrict__ b32, uint8_t* __restrict__ steer, int exclusive_words, int64_t n_words) {
     const int m = blockIdx.x;
     const int64_t lo = seg_off ? seg_off[m] : (int64_t)m * segs_per_map;
     const int64_t hi = seg_off ? seg_off[m + 1] : lo + segs_per_map;
@@ -119,6 +120,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
     pts += 4 * base;
     if (v64) v64 += base;
     if (v32) v32 += base;
+    if (steer) steer += base;
     int i = 32 * warp + lane;
     TIN a0 = TIN(0), a1 = TIN(0), b0 = TIN(0), b1 = TIN(0);
 #if PPNET_VPREFETCH
@@ -127,7 +129,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
 
     for (int t0 = 0; t0 == 0 || t0 < cnt; t0 += kCircTile) {
         const int nt = max(0, min(kCircTile, cnt - t0));
-        const bool first_tile = t0 == 0;
+        const bool first_tile = t0 == 0, last_tile = t0 + kCircTile >= cnt;
         __syncthreads();
         for (int t = threadIdx.x; t < 4 * kBins; t += kVThreads) {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -292,6 +294,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     for (int t = min(room, __popc(cw)); t > 0; --t, --room) {                   \
                         const int b = __ffs(cw) - 1;                                            \
                         cw &= cw - 1;                                                           \
+                        PPNET_ASSERT(qp < &queue[warp][0] + kVQueue && basej + b < nt);         \
                         *qp++ = (uint16_t)(tag | (basej + b));                                  \
                     }
                     PPNET_DRAIN(c0, 0)
@@ -307,6 +310,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     if (k < total) {
                         const int e = queue[warp][k];
                         const int owner = e >> 8, j = e & 127;
+                        PPNET_ASSERT(total <= kVQueue && owner < 32 && j < nt);
                         const uint32_t obit = 1u << owner;
                         const bool need64 = DO64 && !(hm64 & obit), need32 = DO32 && !(hm32 & obit);
                         if (need64 || need32) {
@@ -345,6 +349,13 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             if (DO32) {
                 const bool h = (hm32 >> lane) & 1u;
                 if (v32 && have && (first_tile || h)) v32[cur] = h ? 1 : 0;
+                if (steer && have && last_tile) {
+                    // steerTo (neuralplanner.py:86-92): dist = euclidean(start, end) in f32 (un-fused); 0 iff dist > 0 and
+                    // blocked.  sqrt(x) > 0 <=> x > 0 (NaN stays false), so the root itself is not needed.
+                    const float x = __fsub_rn(fs0, fe0), y = __fsub_rn(fs1, fe1);
+                    const float d2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+                    steer[cur] = (d2 > 0.0f && h) ? 0 : 1;
+                }
                 if (b32 && lane == 0) vbits_or(b32, base + batch, hm32 & valid, exclusive_words != 0, first_tile);
             }
             __syncwarp();
@@ -360,7 +371,7 @@ template <bool DO64, bool DO32, typename TIN>
 static int launch_verdict(const TIN* pts, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, int64_t n_maps,
                           const double* obs, const int32_t* obs_cnt, int32_t omax, double clearance, double bound,
                           int32_t dot_mode, int32_t cmp_mode, uint8_t* v64, uint8_t* v32, uint32_t* b64, uint32_t* b32,
-                          cudaStream_t st) {
+                          uint8_t* steer, cudaStream_t st) {
     const int64_t per_map = segs_per_map > 0 ? segs_per_map : n_segs;
     int64_t chunk = 8192;
     while (chunk > kVThreads && n_maps * ((per_map + chunk - 1) / chunk) < 8 * kNumSMs) chunk >>= 1;
@@ -383,11 +394,11 @@ static int launch_verdict(const TIN* pts, int64_t n_segs, const int64_t* seg_off
     if (dot_mode == PPNET_DOT_UNFUSED)
         verdict_kernel<PPNET_DOT_UNFUSED, DO64, DO32, TIN><<<grid, kVThreads, pad, st>>>(
             pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (TIN)bound, cmp_mode, v64, v32, b64, b32,
-            exclusive, n_words);
+            steer, exclusive, n_words);
     else
         verdict_kernel<PPNET_DOT_FUSED_SKX, DO64, DO32, TIN><<<grid, kVThreads, pad, st>>>(
             pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (TIN)bound, cmp_mode, v64, v32, b64, b32,
-            exclusive, n_words);
+            steer, exclusive, n_words);
     PPNET_LAUNCH_CHECK("verdict_kernel");
     return PPNET_OK;
 }
@@ -412,10 +423,29 @@ extern "C" int ppnet_verdict_fused(const double* pts_rc, int64_t n_segs, const i
     cudaStream_t st = (cudaStream_t)stream;
     if (want64 && want32)
         return launch_verdict<true, true, double>(pts_rc, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, clearance,
-                                                  bound, dot_mode, cmp_mode, verdict_f64, verdict_f32, vbits_f64, vbits_f32, st);
+                                                  bound, dot_mode, cmp_mode, verdict_f64, verdict_f32, vbits_f64, vbits_f32, nullptr, st);
     if (want64)
         return launch_verdict<true, false, double>(pts_rc, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, clearance,
-                                                   bound, dot_mode, cmp_mode, verdict_f64, nullptr, vbits_f64, nullptr, st);
+                                                   bound, dot_mode, cmp_mode, verdict_f64, nullptr, vbits_f64, nullptr, nullptr, st);
     return launch_verdict<false, true, double>(pts_rc, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, clearance,
-                                               bound, dot_mode, cmp_mode, nullptr, verdict_f32, nullptr, vbits_f32, st);
+                                               bound, dot_mode, cmp_mode, nullptr, verdict_f32, nullptr, vbits_f32, nullptr, st);
 }
+
+// ---- the one-flavour entry points run the same kernel (one flavour switched off) -------------------------------------
+namespace ppnet {
+int verdict_a11_only(const double* pts_rc, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, int64_t n_maps,
+                     const double* obs, const int32_t* obs_cnt, int32_t omax, double clearance, double bound, int32_t dot_mode,
+                     uint8_t* verdict, cudaStream_t st) {
+    return launch_verdict<true, false, double>(pts_rc, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, clearance, bound,
+                                               dot_mode, PPNET_CMP_F32_NEP50, verdict, nullptr, nullptr, nullptr, nullptr, st);
+}
+int verdict_a12_only(const float* pts_xy, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, int64_t n_maps,
+                     const double* obs, const int32_t* obs_cnt, int32_t omax, double clearance, double bound, int32_t cmp_mode,
+                     uint8_t* verdict, uint8_t* steer, uint8_t* scratch, cudaStream_t st) {
+    // more than one circle tile needs the verdict bytes as the state between tiles: `scratch` stands in when the caller
+    // only asked for steer
+    return launch_verdict<false, true, float>(pts_xy, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, clearance, bound,
+                                              PPNET_DOT_FUSED_SKX, cmp_mode, nullptr, verdict ? verdict : scratch, nullptr, nullptr,
+                                              steer, st);
+}
+}  // namespace ppnet

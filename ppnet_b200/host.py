@@ -20,6 +20,28 @@ def _c(a, dt, name):
     return a
 
 
+def _seg_off(seg_off, n_segs, n_maps):
+    """CSR offsets as the kernels index with them: int64[n_maps + 1], starting at 0, non-decreasing, ending at n_segs."""
+    if seg_off is None:
+        if n_maps == 0 or n_segs % max(n_maps, 1):
+            raise PPNetError("uniform grouping needs n_segs divisible by n_maps (or pass seg_off)")
+        return None
+    so = _c(seg_off, np.int64, "seg_off")
+    if so.size != n_maps + 1 or (so.size and (so[0] != 0 or so[-1] != n_segs or (np.diff(so) < 0).any())):
+        raise PPNetError("seg_off must be int64[n_maps + 1], start at 0, be non-decreasing and end at n_segs (%d)" % n_segs)
+    return so
+
+
+def _out_arr(a, dt, size, name):
+    """Caller-supplied output array or None -> a checked array (exact dtype / size / contiguity: it is handed to
+    cudaMemcpyAsync as a raw pointer)."""
+    if a is None:
+        return np.empty(size, dtype=dt)
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dt) or not a.flags.c_contiguous or a.size != size or not a.flags.writeable:
+        raise PPNetError("%s must be a writeable C-contiguous %s array with %d elements" % (name, np.dtype(dt), size))
+    return a
+
+
 class HostContext:
     """Two CUDA streams + a grow-only device arena (ppnet_ctx_create)."""
 
@@ -50,8 +72,8 @@ class HostContext:
         pts = _c(pts_rc, np.float64, "pts_rc").reshape(-1, 4)
         ob, oc = _c(obs, np.float64, "obs"), _c(obs_cnt, np.int32, "obs_cnt")
         n, m = len(pts), len(oc)
-        so = _c(seg_off, np.int64, "seg_off") if seg_off is not None else None
-        out = np.empty(n, dtype=np.uint8) if out is None else out
+        so = _seg_off(seg_off, n, m)
+        out = _out_arr(out, np.uint8, n, "out")
         check(lib().ppnet_segcheck_edage_f64_host(self._h, _p(pts), ctypes.c_int64(n), _p(so),
                                                   ctypes.c_int64(0 if so is not None else n // max(m, 1)),
                                                   ctypes.c_int64(m), _p(ob), _p(oc), ctypes.c_int32(ob.shape[1]),
@@ -65,8 +87,10 @@ class HostContext:
         pts = _c(pts_xy, np.float32, "pts_xy").reshape(-1, 4)
         ob, oc = _c(obs, np.float64, "obs"), _c(obs_cnt, np.int32, "obs_cnt")
         n, m = len(pts), len(oc)
-        so = _c(seg_off, np.int64, "seg_off") if seg_off is not None else None
-        out = np.empty(n, dtype=np.uint8) if out is None else out
+        so = _seg_off(seg_off, n, m)
+        out = _out_arr(out, np.uint8, n, "out")
+        if steer is not None:
+            steer = _out_arr(steer, np.uint8, n, "steer")
         check(lib().ppnet_segcheck_mpnet_f32_host(self._h, _p(pts), ctypes.c_int64(n), _p(so),
                                                   ctypes.c_int64(0 if so is not None else n // max(m, 1)),
                                                   ctypes.c_int64(m), _p(ob), _p(oc), ctypes.c_int32(ob.shape[1]),
@@ -94,9 +118,11 @@ class HostContext:
         if b.dtype not in (np.uint32, np.int32) or not b.flags.c_contiguous:
             raise PPNetError("bits must be a C-contiguous uint32 array")
         sg = _c(segs_xy, np.float32, "segs_xy").reshape(-1, 4)
-        so = _c(seg_off, np.int64, "seg_off") if seg_off is not None else None
         n, m = len(sg), b.shape[0]
-        out = np.empty(n, dtype=np.uint8) if out is None else out
+        so = _seg_off(seg_off, n, m)
+        out = _out_arr(out, np.uint8, n, "out")
+        if first_hit is not None:
+            first_hit = _out_arr(first_hit, np.int32, n, "first_hit")
         check(lib().ppnet_dda_gridcheck_host(self._h, _p(b), ctypes.c_int32(resolution), ctypes.c_int64(m), _p(sg),
                                              ctypes.c_int64(n), _p(so),
                                              ctypes.c_int64(0 if so is not None else n // max(m, 1)), _p(out),
@@ -107,7 +133,7 @@ class HostContext:
     def gmm_sample(self, seed, sample0, n, mean, std, weights, out=None):
         mean, std, w = _c(mean, np.float32, "mean"), _c(std, np.float32, "std"), _c(weights, np.float32, "weights")
         k, d = mean.shape
-        out = np.empty([n, d], dtype=np.float32) if out is None else out
+        out = _out_arr(out, np.float32, n * d, "out").reshape(n, d) if out is not None else np.empty([n, d], dtype=np.float32)
         check(lib().ppnet_gmm_sample_host(self._h, ctypes.c_uint64(seed), ctypes.c_uint64(sample0), ctypes.c_int64(n),
                                           ctypes.c_int32(k), ctypes.c_int32(d), _p(mean), _p(std), _p(w), _p(out)),
               "ppnet_gmm_sample_host")

@@ -14,24 +14,42 @@ from . import ops
 clearance = 1 / 50 * 224
 obc = []
 
-_cache = {"key": None, "obs": None, "cnt": None}
+_snapshot = {"obs": None, "cnt": None}
+
+
+def _pack(problems):
+    """[[x, y, r], ...] per problem -> (obs f64[P, omax, 3], cnt i32[P]) on the GPU."""
+    if not torch.cuda.is_available():
+        raise ops.PPNetError("ppnet_b200 needs a CUDA device (there is no CPU path)")
+    omax = max([len(o) for o in problems] + [1])
+    arr = np.zeros([max(len(problems), 1), omax, 3])
+    cnt = np.zeros(max(len(problems), 1), dtype=np.int32)
+    for i, o in enumerate(problems):
+        cnt[i] = len(o)
+        if len(o):
+            arr[i, :len(o)] = np.asarray(o, dtype=np.float64).reshape(-1, 3)
+    return torch.from_numpy(arr).cuda(), torch.from_numpy(cnt).cuda()
+
+
+def set_obc(problems=None):
+    """Explicit device snapshot of the obstacle lists for the *_batch entry points (`problems` defaults to the module
+    global `obc`).  The reference-signature functions below do NOT use it: like the reference they read `obc[idx]` at
+    every call, so in-place edits of `obc` are always seen."""
+    src = obc if problems is None else problems
+    _snapshot["obs"], _snapshot["cnt"] = _pack(src)
+    return _snapshot["obs"], _snapshot["cnt"]
 
 
 def _device_obc():
-    """obc as obs f64[P, omax, 3] + cnt on the GPU (re-uploaded when the global is rebound or resized)."""
-    key = (id(obc), len(obc))
-    if _cache["key"] != key:
-        if not torch.cuda.is_available():
-            raise ops.PPNetError("ppnet_b200 needs a CUDA device (there is no CPU path)")
-        omax = max([len(o) for o in obc] + [1])
-        arr = np.zeros([max(len(obc), 1), omax, 3])
-        cnt = np.zeros(max(len(obc), 1), dtype=np.int32)
-        for i, o in enumerate(obc):
-            cnt[i] = len(o)
-            if len(o):
-                arr[i, :len(o)] = np.asarray(o, dtype=np.float64).reshape(-1, 3)
-        _cache.update(key=key, obs=torch.from_numpy(arr).cuda(), cnt=torch.from_numpy(cnt).cuda())
-    return _cache["obs"], _cache["cnt"]
+    """Batch entry points: the snapshot taken by set_obc(), or a fresh upload of the whole global."""
+    if _snapshot["obs"] is not None:
+        return _snapshot["obs"], _snapshot["cnt"]
+    return _pack(obc)
+
+
+def _problem(idx):
+    """obc[idx] read live (neuralplanner.py:52 `for ox, oy, size in obc[idx]`) -> (obs f64[1, n, 3], cnt i32[1])."""
+    return _pack([obc[idx]])
 
 
 def _f32(p):
@@ -41,10 +59,10 @@ def _f32(p):
 
 
 def _one(s, e, idx, want_steer):
-    obs, cnt = _device_obc()
+    obs, cnt = _problem(idx)
     s, e = _f32(s), _f32(e)
     pts = torch.from_numpy(np.asarray([[s[0], s[1], e[0], e[1]]], dtype=np.float32)).cuda()
-    return ops.segcheck_mpnet_f32(pts, obs[idx:idx + 1], cnt[idx:idx + 1], clearance, want_steer=want_steer)
+    return ops.segcheck_mpnet_f32(pts, obs, cnt, clearance, want_steer=want_steer)
 
 
 def collision_check_circle_edge(s, e, idx):
@@ -60,12 +78,12 @@ def steerTo(start, end, idx):
 def _path_tensors(path, idx):
     wp = np.stack([_f32(p)[:2] for p in path]).astype(np.float32)
     off = torch.tensor([0, len(wp)], dtype=torch.int64).cuda()
-    return torch.from_numpy(wp).cuda(), off, torch.tensor([idx], dtype=torch.int32).cuda()
+    return torch.from_numpy(wp).cuda(), off, torch.tensor([0], dtype=torch.int32).cuda()
 
 
 def feasibility_check(path, idx):
     """neuralplanner.py:96-102 -> 1 if every consecutive pair steers, else 0."""
-    obs, cnt = _device_obc()
+    obs, cnt = _problem(idx)
     wp, off, pm = _path_tensors(path, idx)
     return int(ops.path_feasible_f32(wp, off, pm, obs, cnt, clearance)[0].item())
 
@@ -74,7 +92,7 @@ def lvc(path, idx):
     """neuralplanner.py:123-138 (lazy vertex contraction) -> the contracted list of float32 waypoint tensors."""
     if len(path) < 2:
         return path
-    obs, cnt = _device_obc()
+    obs, cnt = _problem(idx)
     wp, off, pm = _path_tensors(path, idx)
     out, n = ops.lvc_f32(wp, off, pm, obs, cnt, clearance)
     out = out[:int(n.item())].cpu()
@@ -82,7 +100,8 @@ def lvc(path, idx):
 
 
 def feasibility_check_batch(wp, path_off, path_map):
-    """Many paths in one launch: wp f32[total,2], CSR offsets, problem index per path -> (feasible u8[P], n_checked)."""
+    """Many paths in one launch: wp f32[total,2], CSR offsets, problem index per path -> (feasible u8[P], n_checked).
+    Obstacles: the set_obc() snapshot if one was taken, else `obc` uploaded afresh."""
     obs, cnt = _device_obc()
     return ops.path_feasible_f32(wp, path_off, path_map, obs, cnt, clearance)
 

@@ -19,6 +19,11 @@ def _stream():
 def _need(t, dtype, name):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise PPNetError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.device.index != torch.cuda.current_device():
+        # the launch goes to the current device's current stream: a tensor elsewhere would fault (or be reached through a
+        # peer mapping from the wrong GPU).  torch.ops.ppnet_b200.* (torch_ops.py) switches devices itself.
+        raise PPNetError("%s lives on %s but the current device is cuda:%d -- wrap the call in torch.cuda.device(%r)"
+                         % (name, t.device, torch.cuda.current_device(), str(t.device)))
     if t.dtype != dtype:
         raise PPNetError("%s must be %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():
@@ -39,8 +44,14 @@ def _seg_grouping(n_segs, n_maps, seg_off):
     _need(seg_off, torch.int64, "seg_off")
     if seg_off.numel() != n_maps + 1:
         raise PPNetError("seg_off must have n_maps + 1 entries")
-    longest = int((seg_off[1:] - seg_off[:-1]).max().item()) if n_maps else 0
-    return seg_off, max(longest, 1)
+    if n_maps:
+        d = seg_off[1:] - seg_off[:-1]
+        lo, hi, first, last = (int(v) for v in torch.stack([d.min(), d.max(), seg_off[0], seg_off[-1]]).tolist())
+        if first != 0 or lo < 0 or last != n_segs:          # the kernels index pts / verdict with it
+            raise PPNetError("seg_off must start at 0, be non-decreasing and end at n_segs (%d)" % n_segs)
+    else:
+        hi = 0
+    return seg_off, max(hi, 1)
 
 
 def segcheck_edage_f64(pts_rc, obs, obs_cnt, clearance, seg_off=None, bound=DEFAULT_BOUND,
@@ -281,8 +292,8 @@ def dda_gridcheck(bits, resolution, segs_xy, seg_off=None, want_first=True, max_
     if seg_off is None:
         so, spm = None, n // max(m, 1)
     else:
-        so = _need(seg_off, torch.int64, "seg_off")
-        spm = max_segs_per_map if max_segs_per_map is not None else max(int((so[1:] - so[:-1]).max().item()), 1)
+        so, longest = _seg_grouping(n, m, seg_off)              # validated: starts at 0, non-decreasing, ends at n
+        spm = max(max_segs_per_map, longest) if max_segs_per_map is not None else longest
     v = torch.empty(n, dtype=torch.uint8, device=bits.device) if out is None else _need(out, torch.uint8, "out")
     fh = None
     if want_first:
@@ -303,8 +314,8 @@ def dda_gridcheck_rc64(bits, resolution, segs_rc, seg_off=None, want=("bits",), 
     if seg_off is None:
         so, spm = None, n // max(m, 1)
     else:
-        so = _need(seg_off, torch.int64, "seg_off")
-        spm = max_segs_per_map if max_segs_per_map is not None else max(int((so[1:] - so[:-1]).max().item()), 1)
+        so, longest = _seg_grouping(n, m, seg_off)              # validated: starts at 0, non-decreasing, ends at n
+        spm = max(max_segs_per_map, longest) if max_segs_per_map is not None else longest
     out = {} if out is None else out
     shapes = {"u8": (n, torch.uint8), "bits": ((n + 31) // 32, torch.int32), "first": (n, torch.int32)}
     for k in want:

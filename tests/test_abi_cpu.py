@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from ppnet_b200 import _lib
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -103,3 +105,17 @@ def test_mirror_modules_import_without_a_gpu_and_refuse_to_compute():
         mpnet.obc = [[]]
         with pytest.raises(PPNetError):
             mpnet.steerTo([1.0, 1.0], [2.0, 2.0], 0)
+
+
+def test_torch_ops_are_registered_and_have_no_cpu_kernel():
+    """torch.ops.ppnet_b200.* (SURVEY 8(b)): registered by the in-tree extension, CUDA dispatch key only."""
+    import torch
+    from ppnet_b200 import torch_ops
+    ns = torch_ops.load()
+    for name in torch_ops.OPS:
+        assert hasattr(ns, name), name
+    with pytest.raises(NotImplementedError):
+        ns.grid_index_f64(torch.zeros(4, dtype=torch.float64), 50.0, 224.0, 112.0)
+    with pytest.raises(NotImplementedError):
+        ns.verdict_fused(torch.zeros([32, 4], dtype=torch.float64), torch.zeros([1, 1, 3], dtype=torch.float64),
+                         torch.zeros([1], dtype=torch.int32), 4.48)

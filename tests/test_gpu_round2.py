@@ -368,3 +368,39 @@ def test_generator_mode_host_pipeline_uploads_nothing():
     fa, fb = int(a["free_count"][0]), int(b["free_count"][0])
     assert fa + fb == int(chk["free_count"][0])
     assert np.array_equal(np.concatenate([a["free_idx"][:fa], b["free_idx"][:fb] + 600 * SPM]), chk["free_idx"][:fa + fb])
+
+
+def test_torch_ops_equal_the_ctypes_ops(ops):
+    """torch.ops.ppnet_b200.* (TORCH_LIBRARY, CUDA key) call the same C ABI as ppnet_b200.ops."""
+    from ppnet_b200 import torch_ops
+    ns = torch_ops.load()
+    rng = np.random.default_rng(31)
+    n_maps, spm = 64, 256
+    segs, obs, cnt = _config2_inputs(rng, n_maps, spm, np.float64)
+    S, Ob, C = dev(segs), dev(obs), dev(cnt)
+    S32 = dev(xy32(segs))
+    b64, b32 = ns.verdict_fused(S, Ob, C, CLEAR)
+    o = ops.verdict_fused(S, Ob, C, CLEAR, want=("bits64", "bits32"))
+    assert torch.equal(b64, o["bits64"]) and torch.equal(b32, o["bits32"])
+    assert torch.equal(ns.segcheck_edage_f64(S, Ob, C, CLEAR), ops.segcheck_edage_f64(S, Ob, C, CLEAR))
+    assert torch.equal(ns.segcheck_mpnet_f32(S32, Ob, C, CLEAR), ops.segcheck_mpnet_f32(S32, Ob, C, CLEAR))
+    bits = ns.raster_circles_bits(Ob, C, 224, 2.24)
+    assert torch.equal(bits, ops.raster_circles_bits(Ob, C, 224, 2.24))
+    wd = ns.dda_gridcheck_rc64(bits, S)
+    assert torch.equal(wd, ops.dda_gridcheck_rc64(bits, 224, S, want=("bits",))["bits"])
+    assert torch.equal(ns.dda_gridcheck(bits, S32), ops.dda_gridcheck(bits, 224, S32, want_first=False))
+    idx, k = ns.compact_bits(b64, b32, wd, len(segs))
+    idx2, k2, _ = ops.compact_bits(b64, b32, wd, n=len(segs))
+    assert int(k.item()) == int(k2.item()) and torch.equal(idx[:int(k.item())], idx2[:int(k.item())])
+    # CSR form: the caller states the longest row
+    lens = rng.integers(0, 200, n_maps)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = int(off[-1])
+    a, b = ns.verdict_fused(S[:n].contiguous(), Ob, C, CLEAR, seg_off=dev(off), max_segs_per_map=int(lens.max()))
+    o = ops.verdict_fused(S[:n].contiguous(), Ob, C, CLEAR, seg_off=dev(off), want=("bits64", "bits32"))
+    assert torch.equal(a, o["bits64"]) and torch.equal(b, o["bits32"])
+    assert torch.equal(ns.propose_segments(S, 7, 100, 8, 64), ops.propose_segments(100, 8, 64, seed=7))
+    pts = dev(rng.uniform(-5, 55, (1000, 2)))
+    assert torch.equal(ns.grid_index_f64(pts, 50.0, 224.0, 112.0), ops.grid_index_f64(pts, 50.0, 224.0, 112.0))
+    with pytest.raises(RuntimeError):
+        ns.verdict_fused(S, Ob, C.long(), CLEAR)                      # wrong dtype is refused, not reinterpreted
