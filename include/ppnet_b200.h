@@ -151,6 +151,14 @@ int ppnet_raster_circles_bits(const double* obs, const int32_t* obs_cnt, int32_t
                               int64_t n_maps, int32_t resolution, double inflate, uint32_t* bits,
                               void* stream);
 
+/* ---- A15, second mode: the canvas model of the same function (matplotlib's default 576 x 432 canvas at dpi 90, data ->
+ *      pixel px = 72 + x / size_w * 446.4, py = 51.84 + y / size_h * 332.64, crop [53:383, 73:517], bilinear resize of the
+ *      330 x 444 crop to R x R, occupied iff the resized value < 0.5).  obs (x, y, r) in the units of `size` (the
+ *      reference passes size = resolution).  Same bit layout as above.  Quantifies the +-1 px gap between the pinned
+ *      geometry and the centre-in-disk rule (anti-aliasing / JPEG / dither still cannot be pinned).                  */
+int ppnet_raster_canvas_bits(const double* obs, const int32_t* obs_cnt, int32_t omax, int64_t n_maps, double size_w,
+                             double size_h, int32_t resolution, double inflate, uint32_t* bits, void* stream);
+
 /* ---- A15 return value + MapGenerate.py:111: image[M][3][R][R] float32, 1 = free / 0 = obstacle from the bit-packed
  *      map, plus `add` (same shape, the placed corridor mask `path_space`; may be NULL).                         */
 int ppnet_bits_to_image(const uint32_t* bits, int32_t resolution, int64_t n_maps, const float* add, float* image,

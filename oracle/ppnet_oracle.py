@@ -877,6 +877,40 @@ def raster_circles_bits(obs, resolution, inflate=0.0):
     return bits
 
 
+# A15, second mode: the CANVAS MODEL of plot_obstacles (EDaGe-PP/Path.py:36-49).  matplotlib's default figure is
+# 6.4 x 4.8 in; savefig(dpi=90) -> 576 x 432 px; default axes [left 0.125, bottom 0.11, width 0.775, height 0.77] ->
+# x in [72, 518.4], y (from the top, y axis inverted by ax.axis(ymin=size[1], ymax=0)) in [51.84, 384.48]; the reference
+# then crops [:, 53:383, 73:517] and T.Resize(resolution)s the 330 x 444 crop (bilinear; torchvision 0.12 of the
+# reference's requirements.txt does not antialias tensors).  Restated: canvas pixel black iff its centre is inside the
+# ELLIPSE a data circle becomes under the two different axis scales; the real torch bilinear resize; occupied iff < 0.5.
+# What is left out is what cannot be pinned here: Agg anti-aliasing, the JPEG round trip and PIL's dither.
+def raster_canvas_bits(obs, size, resolution, inflate=0.0):
+    import torch
+    import torch.nn.functional as F
+    R = int(resolution)
+    W = (R + 31) // 32
+    sx, sy = 446.4 / f64(size[0]), 332.64 / f64(size[1])
+    canvas = np.ones([330, 444], dtype=np.float32)                       # white
+    px = np.arange(73, 517, dtype=np.float64) + 0.5
+    for ox, oy, r in obs:
+        rr = f64(r) + f64(inflate)
+        cx, cy = 72.0 + f64(ox) * sx, 51.84 + f64(oy) * sy
+        if not rr > 0 or not np.isfinite(rr) or not np.isfinite(cx) or not np.isfinite(cy):
+            continue
+        ax, ay = rr * sx, rr * sy
+        for v in range(330):
+            ny = ((f64(53 + v) + 0.5) - cy) / ay
+            nx = (px - cx) / ax
+            canvas[v, (nx * nx + ny * ny) <= 1.0] = 0.0
+    out = F.interpolate(torch.from_numpy(canvas)[None, None], size=(R, R), mode="bilinear", align_corners=False,
+                        antialias=False)[0, 0].numpy()
+    occ = out < 0.5
+    bits = np.zeros([R, W], dtype=np.uint32)
+    for i, j in zip(*np.nonzero(occ)):
+        bits[i, j >> 5] |= np.uint32(1 << (j & 31))
+    return bits
+
+
 # --------------------------------------------------------------------------------------------
 # DDA grid check (NEW functionality in the B200 build; no reference counterpart).
 # Endpoints are snapped with the A4 rule (rint half-even, step 1, offset 0), then an all-integer

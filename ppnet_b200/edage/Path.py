@@ -33,18 +33,30 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+RASTER_MODE = "disk"    # "disk": pixel centre inside the disk (what the generator's bit-packed maps use);
+                        # "canvas": the matplotlib canvas model of Path.py:36-49 (axes affine, crop, bilinear resize)
+
+
 def plot_obstacles(size: tuple, obstacles, resolution: tuple = (224, 224)):
-    """Path.py:36-49 restated geometrically (matplotlib / JPEG / PIL dither are not reproducible): white (1) free,
-    black (0) where a pixel centre lies inside a disk [x, y, r].  -> Tensor[3, H, W] on the GPU."""
+    """Path.py:36-49 restated geometrically (Agg anti-aliasing / JPEG / PIL dither are not reproducible): white (1) free,
+    black (0) obstacle.  RASTER_MODE picks the rule: "disk" = pixel centre inside a disk [x, y, r]; "canvas" = the
+    reference's canvas geometry (ppnet_raster_canvas_bits).  -> Tensor[3, H, W] on the GPU."""
     r = int(resolution[0])
     obs = np.asarray([[float(o[0]), float(o[1]), float(o[2])] for o in obstacles], dtype=np.float64).reshape(-1, 3)
-    scale = r / float(size[0])
     omax = max(len(obs), 1)
     o = torch.zeros([1, omax, 3], dtype=torch.float64, device=_dev())
-    if len(obs):
-        o[0, :len(obs)] = torch.from_numpy(obs * scale).to(o.device)
     cnt = torch.tensor([len(obs)], dtype=torch.int32, device=o.device)
-    bits = ops.raster_circles_bits(o, cnt, r)
+    if RASTER_MODE == "canvas":
+        if len(obs):
+            o[0, :len(obs)] = torch.from_numpy(obs).to(o.device)
+        bits = ops.raster_canvas_bits(o, cnt, (float(size[0]), float(size[1])), r)
+    elif RASTER_MODE == "disk":
+        scale = r / float(size[0])
+        if len(obs):
+            o[0, :len(obs)] = torch.from_numpy(obs * scale).to(o.device)
+        bits = ops.raster_circles_bits(o, cnt, r)
+    else:
+        raise ops.PPNetError("RASTER_MODE must be 'disk' or 'canvas'")
     return ops.bits_to_image(bits, r)[0]
 
 

@@ -283,6 +283,19 @@ def raster_circles_bits(obs, obs_cnt, resolution, inflate=0.0, out=None):
     return bits
 
 
+def raster_canvas_bits(obs, obs_cnt, size, resolution, inflate=0.0):
+    """A15 in the canvas model (ppnet_raster_canvas_bits): obs f64[M,omax,3] in the units of `size` = (w, h)
+    -> bits i32[M,R,ceil(R/32)]."""
+    _need(obs, torch.float64, "obs")
+    _need(obs_cnt, torch.int32, "obs_cnt")
+    m, omax, _ = obs.shape
+    bits = torch.empty([m, resolution, (resolution + 31) // 32], dtype=torch.int32, device=obs.device)
+    check(lib().ppnet_raster_canvas_bits(_ptr(obs), _ptr(obs_cnt), ctypes.c_int32(omax), ctypes.c_int64(m),
+                                         ctypes.c_double(size[0]), ctypes.c_double(size[1]), ctypes.c_int32(resolution),
+                                         ctypes.c_double(inflate), _ptr(bits), _stream()), "ppnet_raster_canvas_bits")
+    return bits
+
+
 def dda_gridcheck(bits, resolution, segs_xy, seg_off=None, want_first=True, max_segs_per_map=None, out=None,
                   first_out=None):
     """Integer DDA vs bit-packed maps: bits i32[M,R,W], segs f32[N,4] grouped by map -> (verdict u8[N], first i32[N])."""

@@ -404,3 +404,41 @@ def test_torch_ops_equal_the_ctypes_ops(ops):
     assert torch.equal(ns.grid_index_f64(pts, 50.0, 224.0, 112.0), ops.grid_index_f64(pts, 50.0, 224.0, 112.0))
     with pytest.raises(RuntimeError):
         ns.verdict_fused(S, Ob, C.long(), CLEAR)                      # wrong dtype is refused, not reinterpreted
+
+
+def test_a15_canvas_model_vs_restatement_and_vs_centre_in_disk(ops):
+    """A15 second mode: the canvas model of plot_obstacles (576 x 432 canvas, axes affine, crop, bilinear resize) equals
+    its numpy + torch restatement pixel for pixel, and its disagreement with the centre-in-disk rule is the +-1 px band
+    SURVEY 8(c) predicted -- quantified per radius class."""
+    rng = np.random.default_rng(15)
+    R, M, O = 224, 24, 20
+    obs = np.zeros([M, O, 3])
+    obs[..., 0] = rng.uniform(-5, R + 5, (M, O))
+    obs[..., 1] = rng.uniform(-5, R + 5, (M, O))
+    obs[..., 2] = rng.uniform(0.2, 22.4, (M, O))
+    obs[3, 0] = [np.nan, 5, 3]
+    obs[3, 1] = [50, 50, 0.0]
+    cnt = rng.integers(0, O + 1, M).astype(np.int32)
+    cnt[:4] = O
+    got = ops.raster_canvas_bits(dev(obs), dev(cnt), (R, R), R, 0.0).cpu().numpy().view(np.uint32)
+    for m in range(M):
+        want = orc.raster_canvas_bits(obs[m, :cnt[m]].tolist(), (R, R), R)
+        assert np.array_equal(got[m], want), m
+    # one circle per map, by radius class: pixels where the two A15 modes disagree, relative to the disk's perimeter
+    report = {}
+    for lo, hi in ((1, 3), (3, 8), (8, 16), (16, 23)):
+        n = 200
+        one = np.zeros([n, 1, 3])
+        one[:, 0, 0] = rng.uniform(30, R - 30, n)
+        one[:, 0, 1] = rng.uniform(30, R - 30, n)
+        one[:, 0, 2] = rng.uniform(lo, hi, n)
+        c1 = np.ones(n, dtype=np.int32)
+        a = ops.raster_canvas_bits(dev(one), dev(c1), (R, R), R, 0.0)
+        b = ops.raster_circles_bits(dev(one), dev(c1), R, 0.0)
+        diff = unpack((a ^ b).cpu().numpy().reshape(-1), n * R * 7 * 32).reshape(n, -1).sum(axis=1)
+        area = unpack(b.cpu().numpy().reshape(-1), n * R * 7 * 32).reshape(n, -1).sum(axis=1)
+        perim = 2 * np.pi * one[:, 0, 2]
+        report[(lo, hi)] = (float(diff.mean()), float((diff / perim).mean()), float(area.mean()))
+        assert (diff / perim).mean() < 1.0, report                    # under one pixel of disagreement per perimeter pixel
+        assert diff.max() > 0                                         # the modes are genuinely different rasters
+    print("A15 canvas vs centre-in-disk, (radius class) -> (pixels differing, per perimeter px, disk area):", report)

@@ -56,3 +56,19 @@ def test_hull_is_convex_ccw_and_contains_every_point(pts):
             assert (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]) > 0      # strict left turns: CCW, no collinear vertex
             for q in p:                                                                       # every point on the inner side of every edge
                 assert (b[0] - a[0]) * (q[1] - a[1]) - (b[1] - a[1]) * (q[0] - a[0]) >= 0
+
+
+def test_a15_canvas_model_affine_and_size():
+    """The canvas-model restatement of plot_obstacles: a disk in the middle of the map comes out as a disk of the same
+    area (to the +-1 px band), shifted by less than a pixel; nothing outside the map paints anything."""
+    from oracle import ppnet_oracle as orc
+    R = 224
+    bits = orc.raster_canvas_bits([[112.0, 112.0, 20.0]], (R, R), R)
+    occ = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(R, -1)[:, :R]
+    ii, jj = np.nonzero(occ)
+    assert abs(occ.sum() - np.pi * 400) < 2 * np.pi * 20                 # area within one perimeter's worth of pixels
+    assert abs(ii.mean() + 0.5 - 112) < 1.0 and abs(jj.mean() + 0.5 - 112) < 1.0
+    ref = orc.raster_circles_bits([[112.0, 112.0, 20.0]], R)
+    disk = ((ref[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(R, -1)[:, :R]
+    assert 0 < (occ != disk).sum() < 2 * np.pi * 20
+    assert orc.raster_canvas_bits([[-60.0, 40.0, 10.0], [float("nan"), 1.0, 1.0]], (R, R), R).sum() == 0
