@@ -347,6 +347,14 @@ int ppnet_propose_segments(uint64_t seed, uint64_t map0, int64_t n_maps, int64_t
 int ppnet_digest_u32(const uint32_t* data, int64_t words_per_unit, int64_t n_units, uint64_t unit0,
                      const int32_t* rows, int32_t row_words, uint64_t salt, uint64_t* acc, void* stream);
 
+/* ---- N1 dataset writer (host code): MapGenerate.generate_map_randomly's record file, EDaGe-PP/MapGenerate.py:144-149.
+ *      One JSON line per problem {"Index", "Init", "End", "Length", "Obstacles"}, byte for byte what json.dumps writes
+ *      (floats as Python's repr).  HOST pointers: index[n], init / end [n][2], length[n], obs[n][omax][3] (first obs_cnt[n]
+ *      rows).  Appends to `path` when append != 0.                                                                   */
+int ppnet_write_problems_jsonl(const char* path, int32_t append, int64_t n, const int64_t* index, const double* init,
+                               const double* end, const double* length, const double* obs, const int32_t* obs_cnt,
+                               int32_t omax, int64_t* out_bytes);
+
 /* ---- host-buffer boundary (e2e): HOST pointers, copies inside, synchronous on return.          */
 int ppnet_ctx_create(int32_t device, void** ctx);
 int ppnet_ctx_destroy(void* ctx);

@@ -30,7 +30,18 @@ class MapGenerate:
         self.PathGroup.generate(path_seg_num=PATHSEGNUM, poly_order=ORDER, dim=DIM, clearance=clearance)
         self.MapLabel = []
         self.Maps = None              # last ops.MapBatch (device): labels, obstacle sets, bit-packed occupancy
-        self.Problems = []            # the unsolved_problems.txt records of the last generate()
+        self._problems, self._problems_list = None, []
+
+    @property
+    def Problems(self):
+        """The unsolved_problems.txt records of the last generate() as dicts (built on first access)."""
+        if self._problems_list is None:
+            pr = self._problems
+            oc = pr["obs_cnt"].tolist()
+            self._problems_list = [{"Index": i, "Init": a, "End": b, "Length": l, "Obstacles": o[:c]} for i, a, b, l, o, c in
+                                   zip(pr["index"].tolist(), pr["init"].tolist(), pr["end"].tolist(), pr["length"].tolist(),
+                                       pr["obs"].tolist(), oc)]
+        return self._problems_list
 
     def generate(self, map_num=100, folder_path='./', round_index=0, *, write_problems=True, save_images=False,
                  max_tries=1000000):
@@ -51,29 +62,37 @@ class MapGenerate:
         gen = ops.generate_maps(bank, 0, n_maps, P, self.ObstaclesNum, R, float(self.MapSize), float(self.ObstacleSize),
                                 float(self.Clearance), seed=seed, max_tries=min(int(max_tries), 2 ** 31 - 1), want_bits=True)
         self.Maps = gen
+        # ONE device->host transfer per array, then everything below is array slicing: no per-map Python arithmetic
         host = {k: getattr(gen, k).cpu().numpy() for k in ("angle", "trans", "segpt", "pathpt", "obs", "obs_cnt", "valid")}
         labels = [[[seg.Poly, seg.EndPoint] for seg in tp.PathSeg] for tp in self.PathGroup.TargetPaths]
-        self.Problems = []
-        lines = []
-        for g in range(n_maps):
-            if not host["valid"][g]:                       # retry budget exhausted (reference: print + break)
+        valid = host["valid"].astype(bool)
+        if not valid.all():                                # retry budget exhausted (reference: print + break)
+            for _ in range(int((~valid).sum())):
                 print('Error:Repeated over {} times! path:'.format(max_tries), folder_path)
-                continue
-            j = (g // P) % P
-            segpoint, pathpoint = host["segpt"][g], host["pathpt"][g]
-            self.MapLabel.append([labels[j], np.array([host["angle"][g]]), [int(host["trans"][g][0]), int(host["trans"][g][1])],
-                                  segpoint, pathpoint])
-            if cnt < total_record:
-                obstacles = [[float(o[0]), float(o[1]), float(o[2])] for o in host["obs"][g][:host["obs_cnt"][g]]]
-                problem = {"Index": g + round_index * 100, "Init": [float(v) for v in segpoint[0]],
-                           "End": [float(v) for v in segpoint[-1]], "Length": self.PathGroup.TargetPaths[j].Length,
-                           "Obstacles": obstacles}
-                self.Problems.append(problem)
-                lines.append(json.dumps(problem))
-                cnt += 1
-        if write_problems and lines:
-            with open("./unsolved_problems.txt", "a") as f:
-                f.write("\n".join(lines) + "\n")
+            idx = np.nonzero(valid)[0]
+            host = {k: v[idx] for k, v in host.items()}
+        else:
+            idx = np.arange(n_maps)
+        jj = ((idx // P) % P).tolist()                     # index rule MapGenerate.py:68: map g uses target path (g // P) % P
+        ang = host["angle"].reshape(-1, 1)
+        # MapLabel entries [label, angle (1-element array), [t0, t1], segpoint, pathpoint]: rows are views of the downloads
+        self.MapLabel.extend([labels[j], a, t, sp, pp] for j, a, t, sp, pp in
+                             zip(jj, ang, host["trans"].tolist(), host["segpt"], host["pathpt"]))
+        # unsolved_problems.txt records: only the first `total_record` maps of the process are logged (MapGenerate.py:144-149).
+        # The lines are written by the library's native writer straight from the downloaded arrays (byte for byte what
+        # json.dumps produces); `Problems` materialises the same records as dicts only when somebody reads it.
+        n_log = max(0, min(len(idx), total_record - cnt))
+        lengths = np.asarray([tp.Length for tp in self.PathGroup.TargetPaths], dtype=np.float64)
+        self._problems = dict(index=np.ascontiguousarray(idx[:n_log].astype(np.int64) + round_index * 100),
+                              init=np.ascontiguousarray(host["segpt"][:n_log, 0]), end=np.ascontiguousarray(host["segpt"][:n_log, -1]),
+                              length=np.ascontiguousarray(lengths[np.asarray(jj[:n_log], dtype=np.int64)]) if n_log else np.zeros(0),
+                              obs=np.ascontiguousarray(host["obs"][:n_log]), obs_cnt=np.ascontiguousarray(host["obs_cnt"][:n_log]))
+        self._problems_list = None
+        cnt += n_log
+        if write_problems and n_log:
+            pr = self._problems
+            ops.write_problems_jsonl("./unsolved_problems.txt", pr["index"], pr["init"], pr["end"], pr["length"], pr["obs"],
+                                     pr["obs_cnt"], append=True)
         if save_images:
             self.save_images(folder_path)
 

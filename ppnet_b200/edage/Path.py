@@ -113,7 +113,7 @@ class Path:
             out = ops.path_synthesize_checked(self._id, 1, seg_num=self.SegNum, poly_order=self.PolyOrder, clearance=self.Clearance,
                                               map_size=map_size, resolution=resolution, seed=_state.current_seed(), want_space=True,
                                               device=self.device, width_coef=width_coef, **kw)
-            self._b = {k: v.cpu().numpy()[0] for k, v in vars(out).items() if isinstance(v, torch.Tensor)}
+            self._b = {k: v[0] for k, v in out.to_host().items()}
         else:
             self._b = {k: v[index] for k, v in batch.items()}
         self._key = key
@@ -169,8 +169,12 @@ class Path:
         self.SegPointImage = b["segpoint_img"].copy()
         self.PathPoint = b["pathpoint"].copy()
         self.BoundaryPoint = b["boundary"].copy()
-        mask = torch.from_numpy(b["space"].astype(np.float32) / 255.0).to(self.device)
-        self.Space = mask[None].repeat(3, 1, 1)
+        dev_space = getattr(self, "_dev_space", None)            # a PathGroup launch keeps the corridor masks on the device
+        if dev_space is not None and self._key == (int(resolution), float(map_size), 0.2):
+            mask = dev_space.to(torch.float32) / 255.0
+        else:
+            mask = torch.from_numpy(b["space"].astype(np.float32) / 255.0).to(self.device)
+        self.Space = mask[None].expand(3, -1, -1)                # three identical channels (ToTensor of an RGB copy, Path.py:136-137)
         return True, self.Space
 
     def path_obstacles(self, resolution=224, map_size=50, map_offset=112):

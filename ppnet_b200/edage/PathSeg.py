@@ -41,7 +41,7 @@ class PathSeg:
             kw = dict(force_straight=torch.ones([1], dtype=torch.uint8).cuda())
         out = ops.path_synthesize(_state.next_path_ids(1), 1, seg_num=1, poly_order=self.PolyOrder,
                                   seed=_state.current_seed(), **kw)
-        b = {k: v.cpu().numpy() for k, v in vars(out).items() if hasattr(v, "cpu")}
+        b = out.to_host()
         self._fill(b, 0, 0)
         return self.Poly, self.EndPoint
 

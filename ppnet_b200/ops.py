@@ -499,7 +499,16 @@ class PathParams(ctypes.Structure):
 
 
 class PathBatch:
-    """Outputs of one path_synthesize launch (device tensors, one attribute per `ppnet_path_params` output)."""
+    """Outputs of one path_synthesize launch (device tensors, one attribute per `ppnet_path_params` output).  The tensors
+    are views of ONE flat device buffer (`_flat`), so `to_host()` is a single device->host copy."""
+
+    def to_host(self):
+        """-> dict name -> numpy array (views of one host copy of the flat buffer)."""
+        flat = self._flat.cpu().numpy()
+        out = {}
+        for name, (off, nbytes, dt, shape) in self._layout.items():
+            out[name] = flat[off:off + nbytes].view(dt).reshape(shape)
+        return out
 
     def to_bank(self):
         """The target-path bank generate_maps consumes (PathPoint, SegPointImage, ConvexHull, obstacles)."""
@@ -535,11 +544,27 @@ def path_synthesize(path0, n_paths, seg_num=10, poly_order=4, clearance=1.0, map
     p.max_obst_rand = in_obst_rand.shape[1] if in_obst_rand is not None else 0
     if in_hull is not None and in_hull.shape[1] != hmax:
         raise PPNetError("in_hull must be [n, hmax, 2]")
+    # one zeroed flat buffer, 256-byte aligned sub-ranges viewed as the typed outputs (one allocation, one memset, and one
+    # copy when the host mirror wants everything)
+    layout, off = {}, 0
+    np_dt = {torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "u1"}
     for name, dt, shp in _PATH_OUTPUTS:
         if name in ("space_raw", "space") and not want_space:
+            continue
+        shape = shp(dims)
+        nbytes = int(torch.tensor([], dtype=dt).element_size())
+        for d in shape:
+            nbytes *= int(d)
+        layout[name] = (off, nbytes, np_dt[dt], tuple(int(d) for d in shape))
+        off = (off + nbytes + 255) & ~255
+    flat = torch.zeros([max(off, 256)], dtype=torch.uint8, device=device)
+    out._flat, out._layout = flat, layout
+    for name, dt, shp in _PATH_OUTPUTS:
+        if name not in layout:
             setattr(out, name, None)
             continue
-        t = torch.zeros(shp(dims), dtype=dt, device=device)
+        o, nbytes, _, shape = layout[name]
+        t = flat[o:o + nbytes].view(dt).reshape(shape)
         setattr(out, name, t)
         setattr(p, name, t.data_ptr())
     check(lib().ppnet_path_synthesize(ctypes.byref(p), _stream()), "ppnet_path_synthesize")
@@ -558,14 +583,13 @@ def path_synthesize_checked(path0, n_paths, hmax=64, pomax=32, max_obst_iter=256
     its lists grow and its set_obstacles loops until it succeeds (EDaGe-PP/Path.py:463-500)."""
     while True:
         out = path_synthesize(path0, n_paths, hmax=hmax, pomax=pomax, max_obst_iter=max_obst_iter, **kw)
-        st = int(torch.bitwise_or(out.status.max(), 0).item()) if n_paths else 0
-        bits = 0
-        if n_paths:
-            for b in (1, 2, 4, 8):
-                if bool((out.status & b).any().item()):
-                    bits |= b
-            if int(out.hull_cnt.max().item()) > hmax:
-                bits |= 8
+        st = bits = 0
+        if n_paths:                                          # one device read for all the guards
+            s_ = out.status
+            st1, st2, st4, st8, hmx = torch.stack([(s_ & 1).max(), (s_ & 2).max(), (s_ & 4).max(), (s_ & 8).max(),
+                                                   out.hull_cnt.max()]).tolist()
+            bits = (1 if st1 else 0) | (2 if st2 else 0) | (4 if st4 else 0) | (8 if st8 or hmx > hmax else 0)
+            st = bits
         if bits == 0:
             return out
         if bits & 2:
@@ -760,3 +784,27 @@ def digest_maps(gen, acc):
         digest(gen.bits, g0, acc, salt=7)
     digest(gen.valid.view(torch.uint8).to(torch.int32), g0, acc, salt=8)
     return acc
+
+
+def write_problems_jsonl(path, index, init, end, length, obs, obs_cnt, append=True):
+    """N1 dataset writer (ppnet_write_problems_jsonl, host code): one json.dumps-identical line per problem
+    {"Index", "Init", "End", "Length", "Obstacles"} (EDaGe-PP/MapGenerate.py:144-149).  numpy arrays: index i64[n],
+    init / end f64[n,2], length f64[n], obs f64[n,omax,3], obs_cnt i32[n].  -> bytes written."""
+    import numpy as np
+
+    def c(a, dt, name, size):
+        a = np.asarray(a)
+        if a.dtype != np.dtype(dt) or not a.flags.c_contiguous or a.size != size:
+            raise PPNetError("%s must be a C-contiguous %s array with %d elements" % (name, np.dtype(dt), size))
+        return a
+    n = len(np.asarray(index))
+    obs = np.asarray(obs)
+    omax = obs.shape[1] if obs.ndim == 3 else 0
+    index, init, end = c(index, np.int64, "index", n), c(init, np.float64, "init", 2 * n), c(end, np.float64, "end", 2 * n)
+    length, obs, obs_cnt = c(length, np.float64, "length", n), c(obs, np.float64, "obs", 3 * omax * n), c(obs_cnt, np.int32, "obs_cnt", n)
+    nb = ctypes.c_int64()
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    check(lib().ppnet_write_problems_jsonl(str(path).encode(), ctypes.c_int32(1 if append else 0), ctypes.c_int64(n), p(index), p(init),
+                                           p(end), p(length), p(obs), p(obs_cnt), ctypes.c_int32(omax), ctypes.byref(nb)),
+          "ppnet_write_problems_jsonl")
+    return nb.value

@@ -119,3 +119,29 @@ def test_torch_ops_are_registered_and_have_no_cpu_kernel():
     with pytest.raises(NotImplementedError):
         ns.verdict_fused(torch.zeros([32, 4], dtype=torch.float64), torch.zeros([1, 1, 3], dtype=torch.float64),
                          torch.zeros([1], dtype=torch.int32), 4.48)
+
+
+def test_native_problem_writer_is_byte_equal_to_json_dumps(tmp_path):
+    """N1 dataset writer (host code in the C-ABI library, no GPU needed): the lines it appends to unsolved_problems.txt are
+    byte for byte what the reference's json.dumps(problem) writes (EDaGe-PP/MapGenerate.py:144-149) -- floats as repr."""
+    import json
+    import numpy as np
+    from ppnet_b200 import ops
+    rng = np.random.default_rng(0)
+    n, omax = 300, 24
+    vals = np.concatenate([rng.uniform(-300, 300, 4000), 10.0 ** rng.uniform(-12, 22, 2000) * rng.choice([-1, 1], 2000),
+                           np.round(rng.uniform(-50, 50, 500)),
+                           [0.0, -0.0, 1e16, 1e-4, 1e-5, 123456789012345678.0, 0.1, 1 / 3, 5e-324, 1.7976931348623157e308,
+                            9999999999999998.0, 1e15, 99999.99999999999, float("inf"), float("-inf"), float("nan")]])
+    obs = rng.choice(vals, (n, omax, 3))
+    init, end, length = rng.choice(vals, (n, 2)), rng.choice(vals, (n, 2)), rng.choice(vals, n)
+    cnt = rng.integers(0, omax + 1, n).astype(np.int32)
+    index = np.arange(n, dtype=np.int64) * 7 - 3
+    path = tmp_path / "unsolved_problems.txt"
+    half = n // 2
+    nb = ops.write_problems_jsonl(path, index[:half], init[:half], end[:half], length[:half], obs[:half], cnt[:half], append=False)
+    nb += ops.write_problems_jsonl(path, index[half:], init[half:], end[half:], length[half:], obs[half:], cnt[half:], append=True)
+    want = "".join(json.dumps({"Index": int(index[i]), "Init": init[i].tolist(), "End": end[i].tolist(), "Length": float(length[i]),
+                               "Obstacles": obs[i, :cnt[i]].tolist()}) + "\n" for i in range(n))
+    got = path.read_text()
+    assert got == want and nb == len(want.encode())
