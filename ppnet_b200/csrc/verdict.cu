@@ -130,6 +130,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
     for (int t0 = 0; t0 == 0 || t0 < cnt; t0 += kCircTile) {
         const int nt = max(0, min(kCircTile, cnt - t0));
         const bool first_tile = t0 == 0, last_tile = t0 + kCircTile >= cnt;
+        const bool wide = nt > 64;                                 // live / candidate words 2, 3 are zero otherwise
         __syncthreads();
         for (int t = threadIdx.x; t < 4 * kBins; t += kVThreads) {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -211,23 +212,25 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             }
             float L64 = 0.f, es64 = 0.f, L32 = 0.f, es32 = 0.f;
             float fs0 = (float)s0, fs1 = (float)s1, fe0 = (float)e0, fe1 = (float)e1;
+            // |s|_1 + |e|_1 + 1 in float serves both flavours' margins (they carry 10x slack; float overflow -> inf -> verbatim)
+            const float msf = fabsf(fs0) + fabsf(fs1) + fabsf(fe0) + fabsf(fe1) + 1.0f;
             if (DO64) {
-                const double d0 = __dsub_rn((double)e0, (double)s0), d1 = __dsub_rn((double)e1, (double)s1);
-                const double L2 = d0 * d0 + d1 * d1;
-                const double ms = fabs((double)s0) + fabs((double)s1) + fabs((double)e0) + fabs((double)e1) + 1.0;
-                verb64 = !(ms < Filt<double>::lim) || !(L2 > Filt<double>::tiny);
-                L64 = verb64 ? CUDART_NAN_F : sqrtf((float)L2);
-                es64 = (float)(Filt<double>::eps * ms);
+                // d = e - s rounded once in double (as the reference does), everything after it in float: the approximate
+                // |d| (relative error ~2e-7, eps64 = 4e-6 is 20x over it) and the margin
+                const float fd0 = (float)__dsub_rn((double)e0, (double)s0), fd1 = (float)__dsub_rn((double)e1, (double)s1);
+                const float L2 = fd0 * fd0 + fd1 * fd1;
+                verb64 = !(msf < 1e15f) || !(L2 > 1e-30f);
+                L64 = verb64 ? CUDART_NAN_F : sqrtf(L2);
+                es64 = (float)Filt<double>::eps * 1.000001f * msf;
             }
             if (DO32) {
                 // neuralplanner.py:44-47 on (x, y): s[0] < 0 or s[1] > 224 ...
                 oob32 = (fs0 < 0.0f) || (fs1 > (float)bound) || (fe0 < 0.0f) || (fe1 > (float)bound);
                 const float d0 = __fsub_rn(fe0, fs0), d1 = __fsub_rn(fe1, fs1);
                 const float L2 = d0 * d0 + d1 * d1;
-                const float ms = fabsf(fs0) + fabsf(fs1) + fabsf(fe0) + fabsf(fe1) + 1.0f;
-                verb32 = !(ms < Filt<float>::lim) || !(L2 > Filt<float>::tiny);
+                verb32 = !(msf < Filt<float>::lim) || !(L2 > Filt<float>::tiny);
                 L32 = verb32 ? CUDART_NAN_F : sqrtf(L2);
-                es32 = Filt<float>::eps * ms;
+                es32 = Filt<float>::eps * msf;
             }
             i += kVThreads;
 #if PPNET_VPREFETCH
@@ -256,14 +259,26 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     const int np_ = min(16, 1 + (int)(fmaxf(fabsf(dx), fabsf(dy)) * (1.0f / 12.0f)));
                     const float inv = 1.0f / (float)np_;
                     uint32_t n0 = ~0u, n1 = ~0u, n2 = ~0u, n3 = ~0u;       // circles culled by EVERY piece
-                    for (int pc = 0; pc < np_; ++pc) {
-                        const float ta = (float)pc * inv, tb = (float)(pc + 1) * inv;
-                        const float ax = sx + dx * ta, bx = sx + dx * tb, ay = sy + dy * ta, by = sy + dy * tb;
-                        const int x0 = bin_clamp(fminf(ax, bx) - mb), x1 = bin_clamp(fmaxf(ax, bx) + mb);
-                        const int y0 = bin_clamp(fminf(ay, by) - mb), y1 = bin_clamp(fmaxf(ay, by) + mb);
-                        const uint4 p = LT[0][x0], r = GT[0][x1], u = LT[1][y0], v = GT[1][y1];
-                        n0 &= p.x | r.x | u.x | v.x; n1 &= p.y | r.y | u.y | v.y;
-                        n2 &= p.z | r.z | u.z | v.z; n3 &= p.w | r.w | u.w | v.w;
+                    if (wide) {
+                        for (int pc = 0; pc < np_; ++pc) {
+                            const float ta = (float)pc * inv, tb = (float)(pc + 1) * inv;
+                            const float ax = sx + dx * ta, bx = sx + dx * tb, ay = sy + dy * ta, by = sy + dy * tb;
+                            const int x0 = bin_clamp(fminf(ax, bx) - mb), x1 = bin_clamp(fmaxf(ax, bx) + mb);
+                            const int y0 = bin_clamp(fminf(ay, by) - mb), y1 = bin_clamp(fmaxf(ay, by) + mb);
+                            const uint4 p = LT[0][x0], r = GT[0][x1], u = LT[1][y0], v = GT[1][y1];
+                            n0 &= p.x | r.x | u.x | v.x; n1 &= p.y | r.y | u.y | v.y;
+                            n2 &= p.z | r.z | u.z | v.z; n3 &= p.w | r.w | u.w | v.w;
+                        }
+                    } else {                                               // <= 64 circles in this tile: two words, 8-byte loads
+                        for (int pc = 0; pc < np_; ++pc) {
+                            const float ta = (float)pc * inv, tb = (float)(pc + 1) * inv;
+                            const float ax = sx + dx * ta, bx = sx + dx * tb, ay = sy + dy * ta, by = sy + dy * tb;
+                            const int x0 = bin_clamp(fminf(ax, bx) - mb), x1 = bin_clamp(fmaxf(ax, bx) + mb);
+                            const int y0 = bin_clamp(fminf(ay, by) - mb), y1 = bin_clamp(fmaxf(ay, by) + mb);
+                            const uint2 p = *reinterpret_cast<const uint2*>(&LT[0][x0]), r = *reinterpret_cast<const uint2*>(&GT[0][x1]);
+                            const uint2 u = *reinterpret_cast<const uint2*>(&LT[1][y0]), v = *reinterpret_cast<const uint2*>(&GT[1][y1]);
+                            n0 &= p.x | r.x | u.x | v.x; n1 &= p.y | r.y | u.y | v.y;
+                        }
                     }
                     const uint4 od = *reinterpret_cast<const uint4*>(odd_mask);
                     c0 = lv.x & (~n0 | od.x); c1 = lv.y & (~n1 | od.y); c2 = lv.z & (~n2 | od.z); c3 = lv.w & (~n3 | od.w);
@@ -275,8 +290,8 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             // warp-uniform hit masks (bit = owner lane); segments that are already decided start set
             uint32_t hm64 = DO64 ? __ballot_sync(0xffffffffu, hit64 || !have) : ~0u;
             uint32_t hm32 = DO32 ? __ballot_sync(0xffffffffu, hit32 || !have) : ~0u;
-            while (__any_sync(0xffffffffu, (c0 | c1 | c2 | c3) != 0u)) {
-                const int mine = min(kVTake, __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3));
+            while (__any_sync(0xffffffffu, (c0 | c1 | c2 | c3) != 0u)) {       // (c2 = c3 = 0 when !wide)
+                const int mine = min(kVTake, __popc(c0) + __popc(c1) + (wide ? __popc(c2) + __popc(c3) : 0));
                 int off = mine;                                            // inclusive warp scan
 #pragma unroll
                 for (int sft = 1; sft < 32; sft <<= 1) {
@@ -299,8 +314,10 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     }
                     PPNET_DRAIN(c0, 0)
                     PPNET_DRAIN(c1, 32)
-                    PPNET_DRAIN(c2, 64)
-                    PPNET_DRAIN(c3, 96)
+                    if (wide) {
+                        PPNET_DRAIN(c2, 64)
+                        PPNET_DRAIN(c3, 96)
+                    }
 #undef PPNET_DRAIN
                 }
                 __syncwarp();
