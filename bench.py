@@ -450,11 +450,7 @@ def config4(torch, dist, ops, sharding, rank, world, dev, total_maps, batch=1000
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     _, totals, offs = sharding.gather_counts(counters)
-    dig = [acc]
-    if world > 1:
-        dig = [torch.zeros_like(acc) for _ in range(world)]
-        dist.all_gather(dig, acc)
-    combined = sum(int(d.item()) & 0xFFFFFFFFFFFFFFFF for d in dig) & 0xFFFFFFFFFFFFFFFF
+    combined, _ = sharding.combine_digests(acc)
     assert torch.equal(cnt_digest, counters), "the two passes over the same global range disagree"
     return {"total_maps": int(total_maps), "scaling": "strong", "world": world, "seconds": ms * 1e-3,
             "maps_per_s": total_maps / (ms * 1e-3), "valid_paths_per_s": totals["valid_paths"] / (ms * 1e-3),

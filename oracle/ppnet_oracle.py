@@ -966,3 +966,35 @@ def gmm_marginal_cdf(x, weights, mean, std, dim):
     x = np.asarray(x, dtype=np.float64)[:, None]
     return (w[None, :] * norm.cdf(x, loc=np.asarray(mean)[None, :, dim],
                                    scale=np.asarray(std)[None, :, dim])).sum(axis=1)
+
+
+# --------------------------------------------------------------------------------------------
+# 64-bit content digest (ppnet_b200/csrc/digest.cu): cross-rank identity proof, additive over any split of the global
+# unit range.  digest = sum over units u (global index g = unit0 + u) and 32-bit words k of
+#   mix64(word ^ mix64(mix64(g * 0x9E3779B97F4A7C15 + salt) + k))   (mod 2^64), mix64 = splitmix64 finaliser.
+# --------------------------------------------------------------------------------------------
+def _mix64(x):
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> np.uint64(30)); x = x * np.uint64(0xbf58476d1ce4e5b9)
+        x = x ^ (x >> np.uint64(27)); x = x * np.uint64(0x94d049bb133111eb)
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def digest_u32(data, unit0, rows=None, row_words=0, salt=0):
+    """data: array [n_units, ...] of any dtype whose unit size is a multiple of 4 bytes -> Python int (mod 2^64)."""
+    a = np.ascontiguousarray(data)
+    n = a.shape[0]
+    if n == 0:
+        return 0
+    w = a.reshape(n, -1).view(np.uint32).astype(np.uint64)
+    wpu = w.shape[1]
+    g = np.uint64(unit0) + np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        key = _mix64(g * np.uint64(0x9E3779B97F4A7C15) + np.uint64(salt))
+        m = _mix64(w ^ _mix64(key[:, None] + np.arange(wpu, dtype=np.uint64)[None, :]))
+    if rows is not None:
+        keep = np.arange(wpu)[None, :] < (np.maximum(np.asarray(rows), 0)[:, None] * row_words)
+        m = np.where(keep, m, np.uint64(0))
+    return int(m.sum(dtype=np.uint64))

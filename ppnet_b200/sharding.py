@@ -40,3 +40,19 @@ def gather_counts(counters):
     totals = {n: int(v) for n, v in zip(COUNTER_NAMES, per_rank.sum(0).tolist())}
     offs = per_rank[:rank].sum(0).tolist() if rank else [0] * len(COUNTER_NAMES)
     return per_rank, totals, {n: int(v) for n, v in zip(COUNTER_NAMES, offs)}
+
+
+def combine_digests(digest):
+    """The identity proof's collective: every rank contributes the 64-bit content digest of its shard (an int64 tensor of one
+    element holding the uint64 bits, ppnet_digest_u32 / ops.digest_maps); the digests are all-gathered and summed modulo 2^64.
+    Because the digest is additive over any split of the global map range, the result must not depend on the world size.
+    -> (combined Python int, per-rank list)."""
+    if digest.dtype != torch.int64 or digest.numel() != 1:
+        raise ValueError("digest must be an int64[1] tensor")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        parts = [torch.zeros_like(digest) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, digest.contiguous())
+    else:
+        parts = [digest]
+    per_rank = [int(p.item()) & 0xFFFFFFFFFFFFFFFF for p in parts]
+    return sum(per_rank) & 0xFFFFFFFFFFFFFFFF, per_rank

@@ -442,3 +442,30 @@ def test_a15_canvas_model_vs_restatement_and_vs_centre_in_disk(ops):
         assert (diff / perim).mean() < 1.0, report                    # under one pixel of disagreement per perimeter pixel
         assert diff.max() > 0                                         # the modes are genuinely different rasters
     print("A15 canvas vs centre-in-disk, (radius class) -> (pixels differing, per perimeter px, disk area):", report)
+
+
+def test_content_digest_kernel_vs_restatement_and_additivity(ops):
+    """ppnet_digest_u32 == its numpy restatement, and digest([a, c)) == digest([a, b)) + digest([b, c)) mod 2^64 -- on raw
+    arrays and on real generator output (the property config 4's cross-rank identity proof rests on)."""
+    rng = np.random.default_rng(64)
+    n = 777
+    f64 = rng.normal(0, 100, (n, 5, 2))
+    i32 = rng.integers(-1000, 1000, (n, 3)).astype(np.int32)
+    rows = rng.integers(0, 6, n).astype(np.int32)
+    acc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ops.digest(dev(f64), 1000, acc, salt=3)
+    ops.digest(dev(i32), 1000, acc, salt=9)
+    ops.digest(dev(f64), 1000, acc, rows=dev(rows), row_elems=2, salt=5)
+    want = (orc.digest_u32(f64, 1000, salt=3) + orc.digest_u32(i32, 1000, salt=9) +
+            orc.digest_u32(f64, 1000, rows=rows, row_words=4, salt=5)) & 0xFFFFFFFFFFFFFFFF
+    assert (int(acc.item()) & 0xFFFFFFFFFFFFFFFF) == want
+    bank = ops.path_synthesize(0, 20, clearance=1.0, seed=5, pomax=24).to_bank()
+    whole = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ops.digest_maps(ops.generate_maps(bank, 500, 3000, 10, 50, 224, 50.0, 5.0, 1.0, seed=5, raster_inflate=2.24), whole)
+    parts = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for a, b in ((500, 1203), (1703, 1), (1704, 1796)):
+        ops.digest_maps(ops.generate_maps(bank, a, b, 10, 50, 224, 50.0, 5.0, 1.0, seed=5, raster_inflate=2.24), parts)
+    assert int(whole.item()) == int(parts.item()) != 0
+    other = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ops.digest_maps(ops.generate_maps(bank, 501, 3000, 10, 50, 224, 50.0, 5.0, 1.0, seed=5, raster_inflate=2.24), other)
+    assert int(other.item()) != int(whole.item())                      # a shifted range is a different dataset

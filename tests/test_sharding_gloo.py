@@ -74,3 +74,48 @@ def test_gather_counts_single_process():
     assert per_rank.tolist() == [[5, 4, 200, 11]] and totals["valid_paths"] == 4 and offs["maps"] == 0
     with pytest.raises(ValueError):
         sharding.gather_counts(torch.zeros(3, dtype=torch.int64))
+
+
+def _digest_worker(rank, world, port, total, q):
+    import numpy as np
+    from oracle import ppnet_oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        first, count = sharding.shard_range(total, rank, world)
+        # stand-in for a rank's generated maps: unit g is a pure function of g (as the Philox-keyed generator's outputs are)
+        g = np.arange(first, first + count, dtype=np.int64)
+        data = np.stack([g * 3 + 1, g * g % 1000003, g ^ 0x5555], axis=1).astype(np.int32)
+        rows = (g % 4).astype(np.int32)
+        d = (orc.digest_u32(data, first, salt=4) + orc.digest_u32(data, first, rows=rows, row_words=1, salt=5)) & 0xFFFFFFFFFFFFFFFF
+        signed = d - (1 << 64) if d >= (1 << 63) else d
+        combined, per_rank = sharding.combine_digests(torch.tensor([signed], dtype=torch.int64))
+        q.put((rank, combined, per_rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_digest_combination_is_world_size_invariant_gloo(world):
+    """Config 4's identity proof on the CPU: per-shard digests, all-gathered and summed mod 2^64, equal the digest of the whole
+    range computed by one process (the kernels' digest is checked against the same restatement in the GPU tests)."""
+    import numpy as np
+    from oracle import ppnet_oracle as orc
+    total = 1001
+    g = np.arange(total, dtype=np.int64)
+    data = np.stack([g * 3 + 1, g * g % 1000003, g ^ 0x5555], axis=1).astype(np.int32)
+    want = (orc.digest_u32(data, 0, salt=4) + orc.digest_u32(data, 0, rows=(g % 4).astype(np.int32), row_words=1, salt=5)) & 0xFFFFFFFFFFFFFFFF
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_digest_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, combined, per_rank in got:
+        assert combined == want and len(per_rank) == world
+    assert sharding.combine_digests(torch.tensor([5], dtype=torch.int64)) == (5, [5])
