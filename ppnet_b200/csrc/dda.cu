@@ -28,8 +28,14 @@ __device__ __forceinline__ long long floordiv64(long long num, long long den) { 
     return num >= 0 ? num / den : -((den - 1 - num) / den);
 }
 
-constexpr int kDdaThreads = 256;
-constexpr int kDdaPerThread = 4;
+#ifndef PPNET_DDA_THREADS
+#define PPNET_DDA_THREADS 256
+#endif
+#ifndef PPNET_DDA_PER
+#define PPNET_DDA_PER 4
+#endif
+constexpr int kDdaThreads = PPNET_DDA_THREADS;
+constexpr int kDdaPerThread = PPNET_DDA_PER;
 constexpr int kDdaStage = kDdaThreads * kDdaPerThread;   // segments per stage (16 KB of walk records)
 constexpr int kDdaClaim = 64;                // stage entries a warp claims at a time
 constexpr float kCoordClampF = 536870912.0f; // 2^29

@@ -1,3 +1,5 @@
-mkdir -p gpurun_out
-python scripts/dev_verdict.py 2>&1 | grep -E "fused|old|mismatches [1-9]"
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q 2>&1 | tail -3
+for v in "" 9 10 12; do
+  if [ -n "$v" ]; then export PPNET_B200_LIB=$PWD/ppnet_b200/lib/libvar_gen_$v.so; else unset PPNET_B200_LIB; fi
+  echo "== variant $v"; python bench.py --steps 3 --warmup 3 --passes 8 --no-e2e --no-cpu --no-secondary --no-config4 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('pass %.4f'%d['ms_per_pass'], {k:round(v['ms'],4) for k,v in d['kernels'].items()})"
+done
