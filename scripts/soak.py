@@ -51,6 +51,26 @@ for it in range(rounds):
         vd, fh = ops.dda_gridcheck(bits, R, d(s32), seg_off=d(off))
         wd, wfh = c_oracle.dda_gridcheck(wb, R, s32, seg_map, threads=8)
         assert np.array_equal(vd.cpu().numpy(), wd) and np.array_equal(fh.cpu().numpy(), wfh), ("dda", it, R)
+    # round 2: the fused kernel (both flavours on one read, bytes and bit-packed), the DDA on the f64 array, the compaction
+    with np.errstate(over="ignore", invalid="ignore"):
+        xy = np.ascontiguousarray(segs[:, [1, 0, 3, 2]].astype(np.float32))
+    cmp_mode = int(rng.integers(0, 2))
+    fo = ops.verdict_fused(d(segs), d(obs), d(cnt), clearance, seg_off=d(off), bound=bound, dot_mode=int(it & 1), cmp_mode=cmp_mode,
+                           want=("u8_64", "u8_32", "bits64", "bits32") if it % 3 else ("bits64", "bits32"))
+    w64 = c_oracle.segcheck_f64(segs, seg_map, obs, cnt, clearance, bound=bound, dot_mode=int(it & 1), threads=8)
+    w32 = c_oracle.segcheck_f32_cmp(xy, seg_map, obs, cnt, clearance, cmp_mode, bound=bound, threads=8)
+    for key, want in (("u8_64", w64), ("u8_32", w32), ("bits64", w64), ("bits32", w32)):
+        if key in fo:
+            got = (ops.unpack_bits(fo[key], n) if key.startswith("bits") else fo[key]).cpu().numpy()
+            assert np.array_equal(got, want), ("fused", key, it, R, M, omax, clearance, bound, cmp_mode, np.nonzero(got != want)[0][:5])
+    if R <= 1024:
+        do = ops.dda_gridcheck_rc64(bits, R, d(segs), seg_off=d(off), want=("bits", "u8", "first"))
+        wd2, wf2 = c_oracle.dda_gridcheck(wb, R, xy, seg_map, threads=8)
+        assert np.array_equal(do["u8"].cpu().numpy(), wd2) and np.array_equal(do["first"].cpu().numpy(), wf2), ("dda64", it, R)
+        assert np.array_equal(ops.unpack_bits(do["bits"], n).cpu().numpy(), wd2), ("dda64 bits", it, R)
+        idx, k, _ = ops.compact_bits(fo["bits64"], fo["bits32"], do["bits"], n=n)
+        free = np.nonzero((w64 | w32 | wd2) == 0)[0]
+        assert int(k.item()) == len(free) and np.array_equal(idx[:len(free)].cpu().numpy(), free), ("compact", it)
     tot += n
     print("round %d ok: R=%d M=%d omax=%d n=%d c=%.3g bound=%.3g positives %.2f" % (it, R, M, omax, n, clearance, bound, w.mean()), flush=True)
-print("soak ok:", tot, "segments x 4 checks bit-exact")
+print("soak ok:", tot, "segments x {f64 fused / un-fused, f32 + steer, raster + DDA, fused A11+A12 (both cmp modes), DDA on the f64 array, compaction} bit-exact")
