@@ -39,6 +39,17 @@ struct Ctx {
     cudaEvent_t ev_up[kPipe] = {}, ev_cmp[kPipe] = {}, ev_cnt[kPipe] = {}, ev_down[kPipe] = {};
 };
 
+// An entry point that fails half-way may still have copies into the caller's host buffers in flight on its streams: let
+// them land before the caller sees the error (and possibly frees those buffers).
+static int drain_on_error(Ctx* c, int rc) {
+    if (rc != PPNET_OK && c) {
+        for (int i = 0; i < 2; ++i) if (c->slot[i].st) cudaStreamSynchronize(c->slot[i].st);
+        for (cudaStream_t st : {c->st_up, c->st_cmp, c->st_down}) if (st) cudaStreamSynchronize(st);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
 static int slot_reserve(Slot& s, int i, size_t bytes) {
     if (bytes <= s.cap[i]) return PPNET_OK;
     if (s.buf[i]) {
@@ -77,7 +88,7 @@ static std::vector<Slice> make_slices(int64_t n_segs, const int64_t* seg_off, in
 }
 
 template <typename T, typename Launch>
-static int segcheck_host(Ctx* c, const T* pts, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map,
+static int segcheck_host_run(Ctx* c, const T* pts, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map,
                          int64_t n_maps, const double* obs, const int32_t* obs_cnt, int32_t omax,
                          uint8_t* verdict, uint8_t* steer, Launch launch) {
     PPNET_REQUIRE(c, "host api: null context");
@@ -132,6 +143,12 @@ static int segcheck_host(Ctx* c, const T* pts, int64_t n_segs, const int64_t* se
     return PPNET_OK;
 }
 
+template <typename T, typename Launch>
+static int segcheck_host(Ctx* c, const T* pts, int64_t n_segs, const int64_t* seg_off, int64_t segs_per_map, int64_t n_maps,
+                         const double* obs, const int32_t* obs_cnt, int32_t omax, uint8_t* verdict, uint8_t* steer, Launch launch) {
+    return drain_on_error(c, segcheck_host_run<T>(c, pts, n_segs, seg_off, segs_per_map, n_maps, obs, obs_cnt, omax, verdict, steer, launch));
+}
+
 }  // namespace ppnet
 
 using namespace ppnet;
@@ -141,7 +158,12 @@ extern "C" int ppnet_ctx_create(int32_t device, void** ctx) {
     PPNET_CUDA(cudaSetDevice(device));
     Ctx* c = new Ctx();
     c->device = device;
-    for (int i = 0; i < 2; ++i) PPNET_CUDA(cudaStreamCreateWithFlags(&c->slot[i].st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamCreateWithFlags(&c->slot[i].st, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("ctx_create: cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            ppnet_ctx_destroy(c);                            // frees whatever was created
+            return PPNET_E_CUDA;
+        }
     *ctx = c;
     return PPNET_OK;
 }
@@ -200,10 +222,9 @@ extern "C" int ppnet_segcheck_mpnet_f32_host(void* ctx, const float* pts_xy, int
                                 });
 }
 
-extern "C" int ppnet_clearance_filter_f64_host(void* ctx, const double* pathpt, int32_t np, const double* cand,
-                                               int32_t O, int64_t n_maps, double map_size, double resolution,
-                                               double clearance, uint8_t* accept, double* out, int32_t* out_cnt) {
-    Ctx* c = (Ctx*)ctx;
+static int clearance_host_run(Ctx* c, const double* pathpt, int32_t np, const double* cand,
+                              int32_t O, int64_t n_maps, double map_size, double resolution,
+                              double clearance, uint8_t* accept, double* out, int32_t* out_cnt) {
     PPNET_REQUIRE(c, "host api: null context");
     PPNET_REQUIRE(n_maps >= 0 && np >= 0 && O >= 0, "host api: negative sizes");
     if (n_maps == 0) return PPNET_OK;
@@ -238,6 +259,13 @@ extern "C" int ppnet_clearance_filter_f64_host(void* ctx, const double* pathpt, 
     return PPNET_OK;
 }
 
+extern "C" int ppnet_clearance_filter_f64_host(void* ctx, const double* pathpt, int32_t np, const double* cand,
+                                               int32_t O, int64_t n_maps, double map_size, double resolution,
+                                               double clearance, uint8_t* accept, double* out, int32_t* out_cnt) {
+    return drain_on_error((Ctx*)ctx, clearance_host_run((Ctx*)ctx, pathpt, np, cand, O, n_maps, map_size, resolution, clearance, accept,
+                                                        out, out_cnt));
+}
+
 // ------------------------------------------------------------------------------------------------
 // generate / dda / gmm with host buffers
 // ------------------------------------------------------------------------------------------------
@@ -268,12 +296,15 @@ extern "C" int ppnet_bank_upload(int32_t device, const double* pathpt, const dou
     Bank* b = new Bank();
     b->device = device; b->n_bank = n_bank; b->np = np; b->nseg1 = nseg1; b->hmax = hmax; b->pomax = pomax;
     int rc;
-    if ((rc = upload(&b->pathpt, pathpt, (size_t)n_bank * np * 2)) != PPNET_OK) return rc;
-    if ((rc = upload(&b->segpt, segpt, segpt ? (size_t)n_bank * nseg1 * 2 : 0)) != PPNET_OK) return rc;
-    if ((rc = upload(&b->hull, hull, (size_t)n_bank * hmax * 2)) != PPNET_OK) return rc;
-    if ((rc = upload(&b->hull_cnt, hull_cnt, (size_t)n_bank)) != PPNET_OK) return rc;
-    if ((rc = upload(&b->obs, obs, (size_t)n_bank * pomax * 3)) != PPNET_OK) return rc;
-    if ((rc = upload(&b->obs_cnt, obs_cnt, pomax ? (size_t)n_bank : 0)) != PPNET_OK) return rc;
+    if ((rc = upload(&b->pathpt, pathpt, (size_t)n_bank * np * 2)) != PPNET_OK ||
+        (rc = upload(&b->segpt, segpt, segpt ? (size_t)n_bank * nseg1 * 2 : 0)) != PPNET_OK ||
+        (rc = upload(&b->hull, hull, (size_t)n_bank * hmax * 2)) != PPNET_OK ||
+        (rc = upload(&b->hull_cnt, hull_cnt, (size_t)n_bank)) != PPNET_OK ||
+        (rc = upload(&b->obs, obs, (size_t)n_bank * pomax * 3)) != PPNET_OK ||
+        (rc = upload(&b->obs_cnt, obs_cnt, pomax ? (size_t)n_bank : 0)) != PPNET_OK) {
+        ppnet_bank_free(b);                                  // a partly built bank does not leak its device arrays
+        return rc;
+    }
     *bank = b;
     return PPNET_OK;
 }
@@ -573,15 +604,7 @@ static int generate_host_impl(Ctx* c, Bank* b, const ppnet_gen_params* p, const 
     PPNET_REQUIRE(p->n_maps >= 0, "generate_maps_host: negative n_maps");
     PPNET_REQUIRE(!p->in_angle && !p->in_trans && !p->in_cand, "generate_maps_host: caller-supplied draws need the device API");
     PPNET_CUDA(cudaSetDevice(c->device));
-    const int rc = generate_host_run(c, b, p, io);
-    if (rc != PPNET_OK) {
-        // copies into the caller's buffers may still be in flight on both streams: let them land before the caller
-        // sees the error (and possibly frees those buffers)
-        for (cudaStream_t st : {c->st_up, c->st_cmp, c->st_down})
-            if (st) cudaStreamSynchronize(st);
-        cudaGetLastError();
-    }
-    return rc;
+    return drain_on_error(c, generate_host_run(c, b, p, io));
 }
 
 extern "C" int ppnet_generate_maps_host(void* ctx, void* bank, const ppnet_gen_params* p) {
@@ -594,10 +617,9 @@ extern "C" int ppnet_generate_and_check_host(void* ctx, void* bank, const ppnet_
     return generate_host_impl((Ctx*)ctx, (Bank*)bank, p, io);
 }
 
-extern "C" int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t resolution, int64_t n_maps,
-                                        const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
-                                        int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit) {
-    Ctx* c = (Ctx*)ctx;
+static int dda_host_run(Ctx* c, const uint32_t* bits, int32_t resolution, int64_t n_maps,
+                        const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
+                        int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit) {
     PPNET_REQUIRE(c, "dda_host: null context");
     PPNET_REQUIRE(n_maps >= 0 && n_segs >= 0 && resolution > 0, "dda_host: bad sizes");
     if (n_maps == 0 || n_segs == 0) return PPNET_OK;
@@ -644,9 +666,15 @@ extern "C" int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t
     return PPNET_OK;
 }
 
-extern "C" int ppnet_gmm_sample_host(void* ctx, uint64_t seed, uint64_t sample0, int64_t n, int32_t order, int32_t dim,
-                                     const float* mean, const float* stdv, const float* weights, float* out) {
-    Ctx* c = (Ctx*)ctx;
+extern "C" int ppnet_dda_gridcheck_host(void* ctx, const uint32_t* bits, int32_t resolution, int64_t n_maps,
+                                        const float* segs_xy, int64_t n_segs, const int64_t* seg_off,
+                                        int64_t segs_per_map, uint8_t* verdict, int32_t* first_hit) {
+    return drain_on_error((Ctx*)ctx, dda_host_run((Ctx*)ctx, bits, resolution, n_maps, segs_xy, n_segs, seg_off, segs_per_map, verdict,
+                                                  first_hit));
+}
+
+static int gmm_host_run(Ctx* c, uint64_t seed, uint64_t sample0, int64_t n, int32_t order, int32_t dim,
+                        const float* mean, const float* stdv, const float* weights, float* out) {
     PPNET_REQUIRE(c && mean && stdv && weights && (out || n == 0), "gmm_sample_host: null argument");
     PPNET_REQUIRE(n >= 0 && order > 0 && dim > 0, "gmm_sample_host: bad sizes");
     if (n == 0) return PPNET_OK;
@@ -675,4 +703,9 @@ extern "C" int ppnet_gmm_sample_host(void* ctx, uint64_t seed, uint64_t sample0,
     PPNET_CUDA(cudaStreamSynchronize(c->slot[0].st));
     PPNET_CUDA(cudaStreamSynchronize(c->slot[1].st));
     return PPNET_OK;
+}
+
+extern "C" int ppnet_gmm_sample_host(void* ctx, uint64_t seed, uint64_t sample0, int64_t n, int32_t order, int32_t dim,
+                                     const float* mean, const float* stdv, const float* weights, float* out) {
+    return drain_on_error((Ctx*)ctx, gmm_host_run((Ctx*)ctx, seed, sample0, n, order, dim, mean, stdv, weights, out));
 }

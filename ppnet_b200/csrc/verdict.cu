@@ -18,8 +18,6 @@
 //     of shared-memory atomics; "owner already hit" is a register test.
 //   * "exact only" circles / segments are encoded in the data (margin = +inf / L = NaN fall through every filter
 //     comparison into `edge_exact`), no flag words in the pair loop.
-#include <cstdlib>
-
 #include "segcheck.cuh"
 
 namespace ppnet {
@@ -403,17 +401,12 @@ static int launch_verdict(const TIN* pts, int64_t n_segs, const int64_t* seg_off
         if (b32) PPNET_CUDA(cudaMemsetAsync(b32, 0, 4 * (size_t)n_words, st));
     }
     dim3 grid((unsigned)n_maps, (unsigned)chunks);
-    static const int pad = getenv("PPNET_VERDICT_PAD") ? atoi(getenv("PPNET_VERDICT_PAD")) : 0;   // dev knob: caps resident CTAs
-    if (pad > 0) {
-        cudaFuncSetAttribute(verdict_kernel<PPNET_DOT_UNFUSED, DO64, DO32, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-        cudaFuncSetAttribute(verdict_kernel<PPNET_DOT_FUSED_SKX, DO64, DO32, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-    }
     if (dot_mode == PPNET_DOT_UNFUSED)
-        verdict_kernel<PPNET_DOT_UNFUSED, DO64, DO32, TIN><<<grid, kVThreads, pad, st>>>(
+        verdict_kernel<PPNET_DOT_UNFUSED, DO64, DO32, TIN><<<grid, kVThreads, 0, st>>>(
             pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (TIN)bound, cmp_mode, v64, v32, b64, b32,
             steer, exclusive, n_words);
     else
-        verdict_kernel<PPNET_DOT_FUSED_SKX, DO64, DO32, TIN><<<grid, kVThreads, pad, st>>>(
+        verdict_kernel<PPNET_DOT_FUSED_SKX, DO64, DO32, TIN><<<grid, kVThreads, 0, st>>>(
             pts, seg_off, segs_per_map, (int)chunk, obs, obs_cnt, omax, clearance, (TIN)bound, cmp_mode, v64, v32, b64, b32,
             steer, exclusive, n_words);
     PPNET_LAUNCH_CHECK("verdict_kernel");
