@@ -242,9 +242,17 @@ def reference_config1():
                 t0 = time.perf_counter()
                 mg.generate(map_num=100, folder_path=td + "/", round_index=0)
                 t_maps = time.perf_counter() - t0
+                # a 100-map sample of the clearance filter through generate_map_randomly
+                # (MapGenerate.py:126-151) on the labels just produced
+                t0 = time.perf_counter()
+                for q in range(100):
+                    lab = mg.MapLabel[q]
+                    mg.generate_map_randomly(path_point=lab[4], init=lab[3][0], end=lab[3][10], length=1.0, path_obstacles=[], index=q)
+                t_a14 = time.perf_counter() - t0
         finally:
             os.chdir(cwd)
     return {"paths_s": t_paths, "maps_s": t_maps, "maps": 100, "valid_paths_per_s": 100 / t_maps, "cores": 1,
+            "a14_generate_map_randomly_100_maps_s": t_a14, "a14_obstacle_verdicts_per_s": 100 * 20 / t_a14,
             "excluded": "plot_obstacles (matplotlib is not installed): patched to a white tensor"}
 
 
@@ -375,7 +383,7 @@ def secondary_configs(ops, torch, quick=True):
                                     "avg_circles": float(gen.obs_cnt.float().mean().item())}
     s = rng.uniform(0, Rr, (M * SPM, 2))
     ang = rng.uniform(0, 2 * np.pi, M * SPM)
-    ln = rng.uniform(64, 640, M * SPM)
+    ln = rng.uniform(64, 448, M * SPM)
     e = s + np.stack([np.cos(ang), np.sin(ang)], axis=1) * ln[:, None]
     seg64 = torch.from_numpy(np.concatenate([s, e], axis=1)).cuda()
     o = {}
@@ -496,6 +504,10 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    numa_all = [numa]
+    if world > 1:                                            # every rank's PCIe function, NUMA node and CPU set
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
     M, P = args.maps, args.passes
     n_seg = M * SEGS_PER_MAP
     n_words = (n_seg + 31) // 32
@@ -784,7 +796,7 @@ def run_ours(args):
                     "api": "ppnet_generate_and_check_host, one-array mode (f64 segments uploaded once, float32 flavours derived on the "
                            "device, verdicts bit-packed, valid maps compacted) + ppnet_gmm_sample_host (second context, concurrent); "
                            "pinned host buffers",
-                    "cpu_affinity": numa})
+                    "cpu_affinity": numa_all})
         e2e_gen, _, _ = e2e_run(checks_gen, 40_000)
 
         # the ceiling of this box for these bytes: raw pinned copies of the same volume per pass, both directions at once,

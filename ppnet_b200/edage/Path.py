@@ -123,15 +123,20 @@ class Path:
     def generate(self, show_now=True, polys=None):
         self._polys = polys
         b = self._run() if self._b is None else self._b
+        # the pieces are rows of the path's arrays: one vectorised read per attribute, then plain object construction
+        poly, endp, straight = b["poly"], b["endpoint"].reshape(-1, 1), b["is_straight"].tolist()
+        gst, gend, slen = b["grad_st"], b["grad_end"], b["seg_length"].reshape(-1, 1)
+        rot, trans = b["seg_rot"], b["seg_trans"]
         self.PathSeg = []
         for i in range(self.SegNum):
             seg = PathSeg(self.PolyOrder, self.Dim, is_straight=self.is_straight)
-            seg._fill({k: v[None] for k, v in b.items()}, 0, i)
-            seg.Rotation = b["seg_rot"][i] if i else False
-            seg.Translation = b["seg_trans"][i].copy()
+            seg.Poly, seg.EndPoint, seg.is_straight = poly[i], endp[i], bool(straight[i])
+            seg.GradSt, seg.GradEnd, seg.Length = gst[i], gend[i], slen[i]
+            seg.Rotation = rot[i] if i else False
+            seg.Translation = trans[i]
             self.PathSeg.append(seg)
-        self.SegPoint = b["segpoint_raw"].copy()
-        self.PathPoint = b["pathpoint_raw"].copy()
+        self.SegPoint = b["segpoint_raw"]
+        self.PathPoint = b["pathpoint_raw"]
         self.Length = float(b["length"])
         self.EndPoint = self.SegPoint[-1]
 
@@ -144,7 +149,7 @@ class Path:
         self.Boundary.downboundary.direction = [-p for p in b["up_dir"]]
         self.Boundary.initboundary = [p for p in b["cap_init"]]
         self.Boundary.endboundary = [p for p in b["cap_end"]]
-        self.BoundaryPoint = b["boundary_raw"].copy()
+        self.BoundaryPoint = b["boundary_raw"]
 
     def boundary_check(self, angle, translation):
         hull = np.asarray(self.ConvexHull, dtype=np.float64).reshape(1, -1, 2)
@@ -165,13 +170,13 @@ class Path:
         H = int(b["hull_cnt"])
         self.Rotation = float(b["rotation"])
         self.Translation = [b["translation"][0], b["translation"][1]]
-        self.ConvexHull = torch.from_numpy(b["hull"][:H].copy())
-        self.SegPointImage = b["segpoint_img"].copy()
-        self.PathPoint = b["pathpoint"].copy()
-        self.BoundaryPoint = b["boundary"].copy()
-        dev_space = getattr(self, "_dev_space", None)            # a PathGroup launch keeps the corridor masks on the device
+        self.ConvexHull = torch.from_numpy(b["hull"][:H])
+        self.SegPointImage = b["segpoint_img"]
+        self.PathPoint = b["pathpoint"]
+        self.BoundaryPoint = b["boundary"]
+        dev_space = getattr(self, "_dev_space", None)            # a PathGroup launch keeps the corridor masks (already float, 0..1) on the device
         if dev_space is not None and self._key == (int(resolution), float(map_size), 0.2):
-            mask = dev_space.to(torch.float32) / 255.0
+            mask = dev_space
         else:
             mask = torch.from_numpy(b["space"].astype(np.float32) / 255.0).to(self.device)
         self.Space = mask[None].expand(3, -1, -1)                # three identical channels (ToTensor of an RGB copy, Path.py:136-137)

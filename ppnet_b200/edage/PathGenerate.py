@@ -39,12 +39,13 @@ class PathGroup:
         self.batch = out
         self.bank = out.to_bank()
         host = out.to_host()                               # one device->host copy for everything the Path objects mirror
+        space_f = out.space.to(torch.float32) / 255.0      # the corridor masks as the reference holds them (ToTensor), on the device
         for i in range(self.PathNum):
             path = Path(seg_num=path_seg_num, poly_order=poly_order, dim=dim, clearance=clearance,
                         is_straight=bool(host["path_straight"][i]))
             path._id = first + i
             path._run(self.Resolution, self.MapSize, batch=host, index=i)
-            path._dev_space = out.space[i]
+            path._dev_space = space_f[i]
             path.generate(show_now=False)
             path.draw_boundary(show_now=False)
             rst = path.path_obstacles(resolution=self.Resolution, map_size=self.MapSize, map_offset=self.MapOffset)

@@ -162,3 +162,30 @@ def test_config5_dense_1024_long_paths(ops):
     wd, wfh = c_oracle.dda_gridcheck(bits, R, segs.astype(np.float32), sm, threads=8)
     assert np.array_equal(vd.cpu().numpy(), wd) and np.array_equal(fh.cpu().numpy(), wfh)
     assert 0.3 < v64.mean() <= 1.0 and int(fh.max().item()) > 100
+    # the same resolution, NON-degenerate: 400 small circles (r <= 4 px, clearance 2 px) and segments of 64..448 px, so that
+    # about half of the segments are free and walk their whole length through the 131 KB bitmap (hundreds of cells)
+    CL2, OS2 = 0.4, 0.8
+    c2 = CL2 / MS * R
+    # (unchecked synthesis: with a 2 px clearance set_obstacles hits its iteration guard on some isles -- the reference would
+    # spin there -- and the path-hugging obstacles do not matter for this workload)
+    paths2 = ops.path_synthesize(0, 3, seg_num=S, clearance=CL2, map_size=MS, resolution=R, seed=9, hmax=128, pomax=64)
+    assert int(paths2.hull_cnt.max().item()) <= 128
+    gen2 = ops.generate_maps(paths2.to_bank(), 0, M, 2, O, R, MS, OS2, CL2, seed=9, raster_inflate=c2 / 2, max_tries=1 << 16)
+    assert int(gen2.valid.sum().item()) == M
+    ln2 = rng.uniform(64, 448, M * SPM)
+    e2 = s + np.stack([np.cos(ang), np.sin(ang)], axis=1) * ln2[:, None]
+    segs2 = np.concatenate([s, e2], axis=1)
+    xy2 = np.ascontiguousarray(segs2[:, [1, 0, 3, 2]].astype(np.float32))
+    obs2, cnt2 = gen2.obs.cpu().numpy(), gen2.obs_cnt.cpu().numpy()
+    bits2 = gen2.bits.cpu().numpy().view(np.uint32)
+    D2 = torch.from_numpy(segs2).cuda()
+    fo = ops.verdict_fused(D2, gen2.obs, gen2.obs_cnt, c2, bound=float(R), want=("u8_64", "u8_32"))
+    w64 = c_oracle.segcheck_f64(segs2, sm, obs2, cnt2, c2, bound=float(R), threads=8)
+    w32 = c_oracle.segcheck_f32(xy2, sm, obs2, cnt2, c2, bound=float(R), threads=8, want_steer=False)
+    assert np.array_equal(fo["u8_64"].cpu().numpy(), w64) and np.array_equal(fo["u8_32"].cpu().numpy(), w32)
+    do = ops.dda_gridcheck_rc64(gen2.bits, R, D2, want=("u8", "first"))
+    wd2, wf2 = c_oracle.dda_gridcheck(bits2, R, xy2, sm, threads=8)
+    assert np.array_equal(do["u8"].cpu().numpy(), wd2) and np.array_equal(do["first"].cpu().numpy(), wf2)
+    assert 0.3 < w64.mean() < 0.7 and 0.3 < wd2.mean() < 0.8
+    free_walk = np.maximum(np.abs(np.rint(xy2[:, 2]) - np.rint(xy2[:, 0])), np.abs(np.rint(xy2[:, 3]) - np.rint(xy2[:, 1])))[wd2 == 0]
+    assert free_walk.mean() > 150                              # the free segments really are long walks
