@@ -69,7 +69,11 @@ __device__ __forceinline__ float4 load_seg(const double* segs, int64_t i) {
     return make_float4((float)a.y, (float)a.x, (float)b.y, (float)b.x);
 }
 
-template <typename TS>
+// FIRST = the caller wants the first blocked step.  Without it (verdict only) a segment whose END cell is outside the map
+// or occupied is blocked whatever happens before (cell_n = the end cell; leaving the map earlier is blocked too), so it is
+// resolved at park time like a blocked start cell: a third fewer segments walk, and the ones that no longer do are the
+// partial walks.
+template <typename TS, bool FIRST>
 __global__ void __launch_bounds__(kDdaThreads)
 dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict__ segs,
            const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
@@ -145,6 +149,12 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
             const int a = y0 * RS + x0;
             bool blocked0 = nan || !inside;                                // NaN coordinate or start outside the map: blocked at k = 0
             if (!blocked0) blocked0 = (bm[a >> 5] >> (a & 31)) & 1u;
+            if (!FIRST && !blocked0) {                                     // verdict only: the end cell decides as well
+                const int x1 = x0 + dx, y1 = y0 + dy;                      // (|x0|, |dx| <= 2^30: no overflow)
+                const bool in1 = (unsigned)x1 < (unsigned)R && (unsigned)y1 < (unsigned)R;
+                const int a1 = in1 ? y1 * RS + x1 : 0;
+                blocked0 = !in1 || ((bm[a1 >> 5] >> (a1 & 31)) & 1u);
+            }
             const int adx = abs(dx), ady = abs(dy);
             const int n = max(adx, ady);
             int r0 = blocked0 ? 0 : (n == 0 ? -1 : -2);                    // -2: needs a walk
@@ -292,11 +302,18 @@ static int launch_dda(const uint32_t* bits, int32_t resolution, int64_t n_maps, 
     // a 32-segment flush group owns its output word when every row starts on a multiple of 32
     const int exclusive = (seg_off == nullptr && segs_per_map % 32 == 0) ? 1 : 0;
     if (vbits && !exclusive) PPNET_CUDA(cudaMemsetAsync(vbits, 0, 4 * (size_t)((n_segs + 31) / 32), st));
-    if (smem > 48 * 1024)
-        PPNET_CUDA(cudaFuncSetAttribute(dda_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)n_maps, (unsigned)chunks);
-    dda_kernel<TS><<<grid, kDdaThreads, smem, st>>>(bits, resolution, W, segs, seg_off, segs_per_map, chunk, verdict, first_hit,
-                                                    vbits, exclusive);
+    if (first_hit) {
+        if (smem > 48 * 1024)
+            PPNET_CUDA(cudaFuncSetAttribute(dda_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dda_kernel<TS, true><<<grid, kDdaThreads, smem, st>>>(bits, resolution, W, segs, seg_off, segs_per_map, chunk, verdict,
+                                                              first_hit, vbits, exclusive);
+    } else {
+        if (smem > 48 * 1024)
+            PPNET_CUDA(cudaFuncSetAttribute(dda_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dda_kernel<TS, false><<<grid, kDdaThreads, smem, st>>>(bits, resolution, W, segs, seg_off, segs_per_map, chunk, verdict,
+                                                               nullptr, vbits, exclusive);
+    }
     PPNET_LAUNCH_CHECK("dda_kernel");
     return PPNET_OK;
 }

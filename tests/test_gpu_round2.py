@@ -198,13 +198,16 @@ def test_dda_on_the_a11_array_equals_the_float32_walk(ops):
         s = rng.uniform(-3, R + 3, (n_maps * spm, 2))
         segs = np.concatenate([s, s + rng.normal(0, R / 8, s.shape)], axis=1)
         segs[::211, 0] = np.nan
+        segs[5::307, 2] = 1e20; segs[7::401, 3] = -np.inf; segs[11::503, 1] = 3e9; segs[13::601, 2] = np.nan
         bits = ops.raster_circles_bits(dev(obs), dev(cnt), R, 1.5)
         seg_map = np.repeat(np.arange(n_maps, dtype=np.int32), spm)
-        with np.errstate(invalid="ignore"):
+        with np.errstate(all="ignore"):
             s32 = xy32(segs)
         want_v, want_f = c_oracle.dda_gridcheck(bits.cpu().numpy().view(np.uint32), R, s32, seg_map)
         v32, f32 = ops.dda_gridcheck(bits, R, dev(s32))
         assert np.array_equal(v32.cpu().numpy(), want_v) and np.array_equal(f32.cpu().numpy(), want_f)
+        # verdict only: the kernel variant that also resolves on the END cell at park time
+        assert np.array_equal(ops.dda_gridcheck(bits, R, dev(s32), want_first=False).cpu().numpy(), want_v)
         o = ops.dda_gridcheck_rc64(bits, R, dev(segs), want=("u8", "bits", "first"))
         assert np.array_equal(o["u8"].cpu().numpy(), want_v)
         assert np.array_equal(o["first"].cpu().numpy(), want_f)
