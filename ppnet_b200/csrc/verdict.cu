@@ -26,6 +26,8 @@ constexpr int kVThreads = 128;
 constexpr int kVWarps = kVThreads / 32;
 constexpr int kVQueue = 512;                   // pairs per round of the queue (16 per lane)
 constexpr int kVTake = kVQueue / 32;
+constexpr int kIG = 64;                        // cells per axis of the inner-disk grid (see `inner` in the kernel)
+constexpr int kIGRows = 8;                     // (circle, row) fill tasks per circle and sweep
 
 // smallest float >= t (t finite or inf): (double)x < t  <=>  x < ceil_f32(t) for every float x
 __device__ __forceinline__ float ceil_f32(double t) {
@@ -48,6 +50,9 @@ __device__ __forceinline__ bool flavour_pair(T s0, T s1, T e0, T e1, T L, T es, 
     return fast_pair<T, MODE>(g, c, em, false);
 }
 
+#ifndef PPNET_VPF2
+#define PPNET_VPF2 2
+#endif
 template <typename TIN> struct VOcc;
 #ifndef PPNET_VPREFETCH
 #define PPNET_VPREFETCH 1
@@ -107,10 +112,25 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
     __shared__ float2 sl_a[kVWarps][32];          // (L, es) of the float64 flavour, as floats (NaN L = verbatim)
     __shared__ float2 sl_b[kVWarps][32];          // (L, es) of the float32 flavour
     __shared__ uint16_t queue[kVWarps][kVQueue];
+    // Inner-disk grid: bit (iy, ix) set = the whole cell [ix, ix+1] x [iy, iy+1] * bound/kIG lies inside the disk
+    // |p - o| <= thr - mg of some circle of the tile.  The reference returns True as soon as ONE circle passes the vertex
+    // test euclidean(e, o) < thr (process_map.py:397, neuralplanner.py:54), whatever s is and whatever the other circles do
+    // (no earlier iteration can raise), so a segment whose END point falls in a set cell is blocked in both flavours and
+    // never enters the pair queue (42 % of the config-2 segments have e inside a disk; the 64 x 64 grid catches 33 %, and
+    // they are the segments with the most candidates).  mg = 2 eps32 (2 bound + |o|_1 + thr + 1) + 2e-5 bound covers the
+    // reference's rounding of the distance (<= 50 u32 Mg, e in [0, bound)^2), the float32 rounding of e and of thr in
+    // the float32 flavour, and the float arithmetic of the cell index / the fill below (each <= 1e-6 bound).
+    __shared__ uint32_t inner[kIG][kIG / 32];
+    __shared__ float c_rin[kCircTile];            // thr - mg, <= 0: circle takes no part (dead, odd, no grid)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cnt = min(obs_cnt[m], omax);
     const bool use_grid = bound > TIN(0) && bound < TIN(1e6);
     const float bscale = use_grid ? (float)kBins / (float)bound : 0.0f;
+#ifndef PPNET_VINNER
+#define PPNET_VINNER 1
+#endif
+    const bool use_inner = PPNET_VINNER != 0 && use_grid && (float)bound > 1e-6f;       // keeps every product below finite
+    const float gs = use_inner ? (float)kIG / (float)bound : 0.0f, cw = (float)bound / (float)kIG;
     const double* __restrict__ mobs = obs + (size_t)m * omax * 3;
 
     // CTA-relative 32-bit indices from here on (chunk <= 8192)
@@ -124,6 +144,10 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
 #if PPNET_VPREFETCH
     if (i < n_here) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1);
 #endif
+#if PPNET_VPF2
+    for (int k = 1; k <= PPNET_VPF2; ++k)
+        if (i + k * kVThreads < n_here) asm volatile("prefetch.global.L2 [%0];" ::"l"(pts + 4 * (i + k * kVThreads)));
+#endif
 
     for (int t0 = 0; t0 == 0 || t0 < cnt; t0 += kCircTile) {
         const int nt = max(0, min(kCircTile, cnt - t0));
@@ -135,6 +159,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             (t < 2 * kBins ? &edge_lo[0][0] : &edge_hi[0][0] - 2 * kBins)[t] = z;
         }
         if (threadIdx.x < 4) { live_mask[threadIdx.x] = 0u; odd_mask[threadIdx.x] = 0u; }
+        for (int t = threadIdx.x; t < kIG * kIG / 32; t += kVThreads) (&inner[0][0])[t] = 0u;
         __syncthreads();
         if (threadIdx.x < nt) {
             const int j = threadIdx.x;
@@ -151,6 +176,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             const int w = j >> 5;
             const bool live = DO64 ? thr > 0.0 : thrf > 0.0f;            // thrf > 0 implies thr > 0
             float2 em = make_float2(CUDART_INF_F, CUDART_INF_F);
+            float rin = -1.0f;
             if (live) {
                 atomicOr(&live_mask[w], bit);
                 const double mc = fabs((double)oxf) + fabs((double)oyf) + fabs(thr);
@@ -168,9 +194,13 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     atomicOr(reinterpret_cast<uint32_t*>(&edge_hi[0][x1]) + w, bit);
                     atomicOr(reinterpret_cast<uint32_t*>(&edge_lo[1][y0]) + w, bit);
                     atomicOr(reinterpret_cast<uint32_t*>(&edge_hi[1][y1]) + w, bit);
+                    if (use_inner)
+                        rin = (float)thr * 0.999999f -
+                              (2.0f * Filt<float>::eps * (2.0f * (float)bound + (float)mc + 1.0f) + 2e-5f * (float)bound);
                 }
             }
             c_em[j] = em;
+            c_rin[j] = rin;
         }
         __syncthreads();
         for (int t = threadIdx.x; t < 4 * kBins; t += kVThreads) {   // prefix tables: one (which, axis, bin) entry per thread
@@ -182,6 +212,33 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             } else {
                 for (int b = bin + 1; b < kBins; ++b) { const uint4 q = edge_lo[axis][b]; acc.x |= q.x; acc.y |= q.y; acc.z |= q.z; acc.w |= q.w; }
                 GT[axis][bin] = acc;
+            }
+        }
+        if (use_inner) {
+            // inner-disk grid: kIGRows (circle, cell row) tasks per circle and sweep; every rounding shrinks the span
+            static_assert(kIG == 64, "one 64-bit span mask per row");
+            for (int t = threadIdx.x; t < kIGRows * nt; t += kVThreads) {
+                const int j = t / kIGRows;
+                const float rin = c_rin[j];
+                if (!(rin > 0.0f)) continue;
+                const float2 oc = c_oxy[j];
+                const int iy_lo = (int)fmaxf(floorf((oc.y - rin) * gs), 0.0f);
+                const int iy_hi = (int)fminf(floorf((oc.y + rin) * gs), (float)(kIG - 1));
+                for (int iy = iy_lo + t % kIGRows; iy <= iy_hi; iy += kIGRows) {
+                    const float yl = (float)iy * cw;
+                    const float fy = fmaxf(fabsf(yl - oc.y), fabsf(yl + cw - oc.y));   // farthest y of the row from the centre
+                    const float w2 = rin * rin - fy * fy;
+                    if (!(w2 > 0.0f)) continue;
+                    float hw;
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(hw) : "f"(w2));             // (2 ulp; the factor below is 8 ulp)
+                    hw *= 0.999999f;
+                    const int ix0 = max((int)ceilf((oc.x - hw) * gs + 1e-3f), 0);
+                    const int ix1 = min((int)floorf((oc.x + hw) * gs - 1e-3f) - 1, kIG - 1);
+                    if (ix0 > ix1) continue;
+                    const unsigned long long span = ((2ull << ix1) - 1ull) & ~((1ull << ix0) - 1ull);   // bits ix0..ix1
+                    if ((uint32_t)span) atomicOr(&inner[iy][0], (uint32_t)span);
+                    if ((uint32_t)(span >> 32)) atomicOr(&inner[iy][1], (uint32_t)(span >> 32));
+                }
             }
         }
         __syncthreads();
@@ -234,6 +291,12 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
 #if PPNET_VPREFETCH
             if (i < n_here) Vec4<TIN>::load(pts + 4 * i, a0, a1, b0, b1);     // next batch's load overlaps this one's work
 #endif
+#if PPNET_VPF2
+            // ... and the batches after it are pulled into L2 (no registers): a batch is short since the inner-disk grid decides a
+            // third of the segments up front, and one batch of work no longer covers the DRAM latency
+            if (i + PPNET_VPF2 * kVThreads < n_here)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pts + 4 * (i + PPNET_VPF2 * kVThreads)));
+#endif
             // state of this segment so far (later circle tiles continue from the stored verdict)
             bool hit64 = oob64, hit32 = oob32;
             if (!first_tile) {
@@ -241,6 +304,13 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                 if (DO64) p64 = v64 ? (have && v64[cur] != 0) : ((vbits_load(b64, n_words, base + batch) >> lane) & 1u);
                 if (DO32) p32 = v32 ? (have && v32[cur] != 0) : ((vbits_load(b32, n_words, base + batch) >> lane) & 1u);
                 hit64 = p64 != 0u; hit32 = p32 != 0u;
+            }
+            if (use_inner) {                                       // end point inside a disk with margin: blocked, both flavours
+                const float gx = fe0 * gs, gy = fe1 * gs;
+                if (gx >= 0.0f && gx < (float)kIG && gy >= 0.0f && gy < (float)kIG) {   // (false for NaN)
+                    const int ix = (int)gx, iy = (int)gy;
+                    if (PPNET_VINNER == 1 && (inner[iy][ix >> 5] >> (ix & 31)) & 1u) hit64 = hit32 = true;
+                }
             }
             const bool open = have && ((DO64 && !hit64) || (DO32 && !hit32));
             uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;

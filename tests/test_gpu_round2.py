@@ -187,6 +187,53 @@ def test_a12_cmp_mode_numpy1_vs_nep50(ops):
             assert orc.segcheck_mpnet_f32(segs32[i, :2], segs32[i, 2:], obs[i].tolist(), CLEAR, cmp_mode=mode) == bool(want[i])
 
 
+@pytest.mark.parametrize("bound", [224.0, 33.0, 100.5, 1024.0])
+def test_inner_disk_grid_end_points_around_every_circle_rim(ops, bound):
+    """The verdict kernel resolves a segment whose END point lies in a grid cell that is wholly inside a circle's
+    threshold disk (verdict.cu, `inner`) without looking at any pair.  Sharp cases for that shortcut: end points at
+    distance thr + delta from a centre, delta from -1 px to +0.5 px down to 1e-7 px, end points on the grid's cell
+    corners, circles hanging over the map's border, tiny and huge radii -- a cell marked by mistake would block a
+    segment the reference leaves free.  Bit-exact against the C oracle in both flavours and both cmp modes."""
+    rng = np.random.default_rng(int(bound * 7))
+    n_maps, omax, spm = 96, 24, 2048
+    obs = np.zeros([n_maps, omax, 3])
+    obs[..., 0] = rng.uniform(-0.1 * bound, 1.1 * bound, (n_maps, omax))
+    obs[..., 1] = rng.uniform(-0.1 * bound, 1.1 * bound, (n_maps, omax))
+    obs[..., 2] = rng.uniform(0, bound / 5, (n_maps, omax)) * rng.choice([0.02, 0.3, 1.0], (n_maps, omax))
+    cnt = rng.integers(1, omax + 1, n_maps).astype(np.int32)
+    clear = CLEAR * bound / 224
+    segs = np.empty([n_maps, spm, 4])
+    for m in range(n_maps):
+        j = rng.integers(0, cnt[m], spm)
+        thr = obs[m, j, 2] + clear / 2
+        delta = rng.choice([-1.0, -0.3, -0.12, -0.1, -0.08, -1e-3, -1e-7, 1e-7, 1e-3, 0.5], spm) * rng.uniform(0.5, 1.0, spm)
+        th = rng.uniform(0, 2 * np.pi, spm)
+        ex = obs[m, j, 0] + (thr + delta) * np.cos(th)
+        ey = obs[m, j, 1] + (thr + delta) * np.sin(th)
+        corner = rng.random(spm) < 0.15                         # end points on (or a hair beside) the 64 x 64 cell corners
+        ex[corner] = np.rint(ex[corner] * 64 / bound) * bound / 64 + rng.choice([0.0, 1e-6, -1e-6], corner.sum())
+        ey[corner] = np.rint(ey[corner] * 64 / bound) * bound / 64 + rng.choice([0.0, 1e-6, -1e-6], corner.sum())
+        far = rng.uniform(0, 2 * np.pi, spm)
+        sx = ex + rng.uniform(0.5, bound / 3, spm) * np.cos(far)
+        sy = ey + rng.uniform(0.5, bound / 3, spm) * np.sin(far)
+        segs[m] = np.stack([sy, sx, ey, ex], axis=1)            # (row, col) pairs
+    segs = segs.reshape(-1, 4)
+    segs[::997, 0] = np.nan                                     # a NaN start does not stop the vertex test on e
+    segs[::1499, 1] = 1e12
+    seg_map = np.repeat(np.arange(n_maps, dtype=np.int32), spm)
+    with np.errstate(all="ignore"):
+        s32 = xy32(segs)
+    want64 = c_oracle.segcheck_f64(segs, seg_map, obs, cnt, clear, bound=bound, threads=8)
+    want32 = c_oracle.segcheck_f32(s32, seg_map, obs, cnt, clear, bound=bound, threads=8, want_steer=False)
+    want32c = c_oracle.segcheck_f32_cmp(s32, seg_map, obs, cnt, clear, 1, bound=bound, threads=8)
+    assert 0.2 < want64.mean() < 0.9
+    _check(ops.verdict_fused(dev(segs), dev(obs), dev(cnt), clear, bound=bound, want=ALL), len(segs), want64, want32)
+    _check(ops.verdict_fused(dev(segs), dev(obs), dev(cnt), clear, bound=bound, cmp_mode=ops.CMP_F64_NUMPY1, want=("bits32",)),
+           len(segs), want64, want32c)
+    assert np.array_equal(ops.segcheck_edage_f64(dev(segs), dev(obs), dev(cnt), clear, bound=bound).cpu().numpy(), want64)
+    assert np.array_equal(ops.segcheck_mpnet_f32(dev(s32), dev(obs), dev(cnt), clear, bound=bound).cpu().numpy(), want32)
+
+
 def test_dda_on_the_a11_array_equals_the_float32_walk(ops):
     rng = np.random.default_rng(9)
     for R, n_maps, spm, omax in ((224, 200, 1024, 50), (33, 64, 96, 6), (1024, 6, 4096, 300)):
