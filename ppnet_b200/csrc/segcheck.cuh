@@ -217,6 +217,28 @@ __device__ __forceinline__ bool fast_pair(const FastSeg<T>& g, const Circle<T>& 
     return edge_exact<T, MODE>(g.s0, g.s1, g.e0, g.e1, c.ox, c.oy, c.thr);
 }
 
+// The same decisions with every test computed up front and combined with predicates: in a 32-pair round some lane
+// nearly always reaches the last test, so the early exits of `fast_pair` save no warp instruction, while each of them is a
+// divergence point (BSSY / BSYNC + a branch to resolve) in front of dependent arithmetic.  Only the verbatim replay stays a
+// branch.  NaN / inf operands make every filter comparison false, as above.
+template <typename T, int MODE>
+__device__ __forceinline__ bool fast_pair_bf(T s0, T s1, T e0, T e1, T L, T es, T ox, T oy, T thr, T T2, T em) {
+    using F = FP<T>;
+    const T v0 = F::sub(e0, ox), v1 = F::sub(e1, oy);
+    const bool vert = F::add(F::mul(v0, v0), F::mul(v1, v1)) < T2;     // exact vertex test
+    const T d0 = F::sub(e0, s0), d1 = F::sub(e1, s1);
+    const T L2 = d0 * d0 + d1 * d1;
+    const T q0 = F::sub(ox, s0), q1 = F::sub(oy, s1);
+    const T ac = F::abs_(q0 * d1 - q1 * d0);
+    const T tt = q0 * d0 + q1 * d1;
+    const T del = es + em, dl = del * L;
+    const bool far = ac > (thr + del) * L;
+    const bool out = tt < -dl || tt > L2 + dl;
+    const bool in = ac < (thr - del) * L && tt > dl && tt < L2 - dl;
+    if (vert || far || out || in) return vert || (!far && !out && in);
+    return edge_exact<T, MODE>(s0, s1, e0, e1, ox, oy, thr);
+}
+
 template <typename T> struct Vec4;   // 4 coordinates of one segment
 template <> struct Vec4<double> {
     static __device__ __forceinline__ void load(const double* p, double& a, double& b, double& c, double& d) {

@@ -20,6 +20,10 @@
 //     comparison into `edge_exact`), no flag words in the pair loop.
 #include "segcheck.cuh"
 
+#ifndef PPNET_VBRANCHFREE
+#define PPNET_VBRANCHFREE 1
+#endif
+
 namespace ppnet {
 
 constexpr int kVThreads = 128;
@@ -36,9 +40,26 @@ __device__ __forceinline__ float ceil_f32(double t) {
     return f;
 }
 
+// one MUFU each; relative error <= 2^-22: the margins that absorb the approximate |d| (eps64 = 4e-6, eps32 = 5e-5, see
+// segcheck.cuh) carry 10x over it, and the piece boundaries of the culling query carry 2e-3 bins of slop
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // pair test of one flavour on that flavour's operands (same code path as segcheck.cu's kernel)
 template <typename T, int MODE>
 __device__ __forceinline__ bool flavour_pair(T s0, T s1, T e0, T e1, T L, T es, T ox, T oy, T thr, T T2, T em) {
+#if PPNET_VBRANCHFREE
+    // L = NaN (verbatim-only segment) or em = +inf (odd circle) make every filter comparison false -> edge_exact
+    return fast_pair_bf<T, MODE>(s0, s1, e0, e1, L, es, ox, oy, thr, T2, em);
+#else
     FastSeg<T> g;
     g.s0 = s0; g.s1 = s1; g.e0 = e0; g.e1 = e1; g.L = L; g.es = es;
     g.d0 = FP<T>::sub(e0, s0);
@@ -46,8 +67,8 @@ __device__ __forceinline__ bool flavour_pair(T s0, T s1, T e0, T e1, T L, T es, 
     g.L2 = g.d0 * g.d0 + g.d1 * g.d1;
     Circle<T> c;
     c.ox = ox; c.oy = oy; c.thr = thr; c.T2 = T2;
-    // L = NaN (verbatim-only segment) or em = +inf (odd circle) make every filter comparison false -> edge_exact
     return fast_pair<T, MODE>(g, c, em, false);
+#endif
 }
 
 #ifndef PPNET_VPF2
@@ -165,7 +186,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             const int j = threadIdx.x;
             const double* o = mobs + 3 * (t0 + j);
             const float oxf = (float)o[0], oyf = (float)o[1];            // torch.tensor([ox, oy]) -> float32 centre
-            const double thr = __dadd_rn(o[2], __ddiv_rn(clearance, 2.0));   // size + clearance/2 (Python floats)
+            const double thr = __dadd_rn(o[2], __dmul_rn(clearance, 0.5));   // size + clearance/2 (Python floats; x / 2 == x * 0.5 exactly)
             // float32 flavour: NumPy >= 2 compares the float32 offset with float32(thr) (NEP 50); NumPy 1.x promotes
             // the offset to float64, which for float32 x is  x < ceil_f32(thr)
             const float thrf = cmp64 ? ceil_f32(thr) : (float)thr;
@@ -229,9 +250,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     const float fy = fmaxf(fabsf(yl - oc.y), fabsf(yl + cw - oc.y));   // farthest y of the row from the centre
                     const float w2 = rin * rin - fy * fy;
                     if (!(w2 > 0.0f)) continue;
-                    float hw;
-                    asm("sqrt.approx.f32 %0, %1;" : "=f"(hw) : "f"(w2));             // (2 ulp; the factor below is 8 ulp)
-                    hw *= 0.999999f;
+                    const float hw = sqrt_approx(w2) * 0.999999f;                    // (2 ulp; the factor is 8 ulp)
                     const int ix0 = max((int)ceilf((oc.x - hw) * gs + 1e-3f), 0);
                     const int ix1 = min((int)floorf((oc.x + hw) * gs - 1e-3f) - 1, kIG - 1);
                     if (ix0 > ix1) continue;
@@ -275,7 +294,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                 const float fd0 = (float)__dsub_rn((double)e0, (double)s0), fd1 = (float)__dsub_rn((double)e1, (double)s1);
                 const float L2 = fd0 * fd0 + fd1 * fd1;
                 verb64 = !(msf < 1e15f) || !(L2 > 1e-30f);
-                L64 = verb64 ? CUDART_NAN_F : sqrtf(L2);
+                L64 = verb64 ? CUDART_NAN_F : sqrt_approx(L2);
                 es64 = (float)Filt<double>::eps * 1.000001f * msf;
             }
             if (DO32) {
@@ -284,7 +303,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                 const float d0 = __fsub_rn(fe0, fs0), d1 = __fsub_rn(fe1, fs1);
                 const float L2 = d0 * d0 + d1 * d1;
                 verb32 = !(msf < Filt<float>::lim) || !(L2 > Filt<float>::tiny);
-                L32 = verb32 ? CUDART_NAN_F : sqrtf(L2);
+                L32 = verb32 ? CUDART_NAN_F : sqrt_approx(L2);
                 es32 = Filt<float>::eps * msf;
             }
             i += kVThreads;
@@ -325,7 +344,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     const float dx = (fe0 - fs0) * bscale, dy = (fe1 - fs1) * bscale;
                     const float mb = (DO32 ? es32 * 1.01f : es64) * bscale + 2e-3f;
                     const int np_ = min(16, 1 + (int)(fmaxf(fabsf(dx), fabsf(dy)) * (1.0f / 12.0f)));
-                    const float inv = 1.0f / (float)np_;
+                    const float inv = rcp_approx((float)np_);
                     uint32_t n0 = ~0u, n1 = ~0u, n2 = ~0u, n3 = ~0u;       // circles culled by EVERY piece
                     if (wide) {
                         for (int pc = 0; pc < np_; ++pc) {
@@ -403,6 +422,25 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                             const TIN q_e0 = sl_e0[warp][owner], q_e1 = sl_e1[warp][owner];
                             const float2 oc = c_oxy[j];
                             const float2 em = c_em[j];
+#if PPNET_VBRANCHFREE
+                            // both flavours straight through (independent arithmetic, no divergence point between them); a
+                            // flavour whose owner is already decided just drops its result
+                            bool r64 = false, r32 = false;
+                            if (DO64) {
+                                const float2 la = sl_a[warp][owner];
+                                r64 = flavour_pair<double, MODE>((double)q_s0, (double)q_s1, (double)q_e0, (double)q_e1, (double)la.x,
+                                                                 (double)la.y, (double)oc.x, (double)oc.y, c_thr64[DO64 ? j : 0],
+                                                                 c_T64[DO64 ? j : 0], (double)em.x);
+                            }
+                            if (DO32) {
+                                const float2 lb = sl_b[warp][owner];
+                                const float2 tt = c_t32[DO32 ? j : 0];
+                                r32 = flavour_pair<float, 0>((float)q_s0, (float)q_s1, (float)q_e0, (float)q_e1, lb.x, lb.y, oc.x, oc.y,
+                                                             tt.x, tt.y, em.y);
+                            }
+                            if (need64 && r64) h64 = obit;
+                            if (need32 && r32) h32 = obit;
+#else
                             if (need64) {
                                 const float2 la = sl_a[warp][owner];
                                 if (flavour_pair<double, MODE>((double)q_s0, (double)q_s1, (double)q_e0, (double)q_e1, (double)la.x,
@@ -417,6 +455,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                                                            tt.x, tt.y, em.y))
                                     h32 = obit;
                             }
+#endif
                         }
                     }
                     if (DO64) hm64 |= __reduce_or_sync(0xffffffffu, h64);
