@@ -36,7 +36,7 @@ __device__ __forceinline__ long long floordiv64(long long num, long long den) { 
 #endif
 constexpr int kDdaThreads = PPNET_DDA_THREADS;
 constexpr int kDdaPerThread = PPNET_DDA_PER;
-constexpr int kDdaStage = kDdaThreads * kDdaPerThread;   // segments per stage (16 KB of walk records)
+constexpr int kDdaStage = kDdaThreads * kDdaPerThread;   // segments per stage (32 KB of walk records)
 constexpr int kDdaClaim = 64;                // stage entries a warp claims at a time
 constexpr float kCoordClampF = 536870912.0f; // 2^29
 constexpr int kLaneWalkMaxN = 1 << 28;       // remainders stay inside int32
@@ -91,8 +91,8 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
     if (base >= hi) return;
     const int64_t end = min(hi, base + (int64_t)chunk);
     const uint32_t bytes = (uint32_t)(R * W * 4);
-    int4* stage = reinterpret_cast<int4*>(dsm + 16 + ((bytes + 15u) & ~15u));   // walk records of the parked segments
-    uint16_t* sidx = reinterpret_cast<uint16_t*>(stage + kDdaStage);           // their slot in the stage's result array
+    int4* stage = reinterpret_cast<int4*>(dsm + 16 + ((bytes + 15u) & ~15u));   // walk records of the parked segments (2 x int4 each)
+    uint16_t* sidx = reinterpret_cast<uint16_t*>(stage + 2 * kDdaStage);       // their slot in the stage's result array
     int32_t* res = reinterpret_cast<int32_t*>(sidx + kDdaStage);                // first blocked step per segment, -1 free
     const bool bulk = (bytes & 15u) == 0;
 
@@ -172,10 +172,17 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
                 const int kM = dM > 0 ? R - cM : cM + 1;                   // first k whose major coordinate is outside
                 const int kend = min(n, kM - 1);
                 const int dm = xmaj ? dy : dx;                             // minor-axis delta, |dm| <= n
-                const unsigned flags = (xmaj ? 1u : 0u) | (dM > 0 ? 2u : 0u) | (kM - 1 < n ? 4u : 0u) | (dm < 0 ? 8u : 0u);
                 const int pos = wb + __popc(wm & lt);
                 PPNET_ASSERT(pos >= 0 && pos < kDdaStage && a >= 0 && a < R * RS);
-                stage[pos] = make_int4((int)((unsigned)a | (flags << 28)), kend | ((xmaj ? y0 : x0) << 16), 2 * abs(dm), 2 * n);
+                // the record is stored in the walk's own terms: parking runs with every lane busy, the refill below with a
+                // third of them, so whatever can be derived here is.  Remainder of (2 k d_minor + n) mod 2n kept as a count-up
+                // for either sign: for d_minor < 0 the mirrored remainder 2n - 1 - r starts at n - 1 and wraps exactly when r
+                // would drop below 0.
+                const int sM = (dM > 0 ? 1 : -1) * (xmaj ? 1 : RS);                 // address step of the major axis
+                const int sm = (dm < 0 ? -1 : 1) * (xmaj ? RS : 1);                 // ... of the minor axis when it moves
+                stage[2 * pos] = make_int4(a, kend | ((xmaj ? y0 : x0) << 16), n - (dm < 0 ? 1 : 0),
+                                           kM - 1 < n ? kend + 1 : -1);             // leaves by the major axis next (blocked) / end (free)
+                stage[2 * pos + 1] = make_int4(2 * abs(dm), 2 * n, sM, sm);
                 sidx[pos] = (uint16_t)t;
             }
         }
@@ -206,21 +213,18 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
                     const int my = wnext + __popc(need & lt);
                     if (!live && my < wend) {
                         PPNET_ASSERT(my >= 0 && my < np_ && sidx[my] < ns);
-                        const int4 q = stage[my];
+                        const int4 q = stage[2 * my], w = stage[2 * my + 1];
                         res_ptr = res + sidx[my];
-                        const unsigned flags = (unsigned)q.x >> 28;
-                        a = q.x & 0x0fffffff;
+                        a = q.x;
                         kend = q.y & 0xffff;
                         cm = q.y >> 16;
-                        inc = q.z;                                 // 2 |d_minor|
-                        n2 = q.w;
-                        // remainder of (2 k d_minor + n) mod 2n, kept as a count-up for either sign: for d_minor < 0 the
-                        // mirrored remainder 2n - 1 - r starts at n - 1 and wraps exactly when r would drop below 0
-                        r = (n2 >> 1) - ((flags & 8u) ? 1 : 0);
-                        stepM = ((flags & 2u) ? 1 : -1) * ((flags & 1u) ? 1 : RS);
-                        stepm = ((flags & 8u) ? -1 : 1) * ((flags & 1u) ? RS : 1);
-                        stepc = (flags & 8u) ? -1 : 1;
-                        res_end = (flags & 4u) ? kend + 1 : -1;    // next cell leaves by the major axis (blocked there) / end reached (free)
+                        r = q.z;
+                        res_end = q.w;
+                        inc = w.x;                                 // 2 |d_minor|
+                        n2 = w.y;
+                        stepM = w.z;
+                        stepm = w.w;
+                        stepc = w.w < 0 ? -1 : 1;
                         k = 0;
                         live = true;
                     }
@@ -292,7 +296,7 @@ static int launch_dda(const uint32_t* bits, int32_t resolution, int64_t n_maps, 
     const size_t bm_bytes = (size_t)resolution * W * 4;
     PPNET_REQUIRE((reinterpret_cast<uintptr_t>(bits) & 15) == 0 && (reinterpret_cast<uintptr_t>(segs) & 15) == 0,
                   "dda: bits and segs must be 16-byte aligned");
-    const size_t smem = ((bm_bytes + 15) & ~(size_t)15) + 16 + (size_t)kDdaStage * (16 + 2 + 4);
+    const size_t smem = ((bm_bytes + 15) & ~(size_t)15) + 16 + (size_t)kDdaStage * (32 + 2 + 4);
     PPNET_REQUIRE(smem <= 220 * 1024, "dda: resolution too large for a shared-memory bitmap");
     // big bitmaps: amortise the staging over every segment of the map; small ones: more CTAs in flight
     const int chunk = bm_bytes >= 64 * 1024 ? 8192 : kDdaStage;

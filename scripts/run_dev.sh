@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-python scripts/dev_verdict.py 2>&1 | grep -E "mismatches" | grep -v "mismatches 0"
+python -m pytest tests/test_gpu_round2.py tests/test_gpu_generate.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -4
 for lib in "" $(ls ppnet_b200/lib/libvar_*.so 2>/dev/null); do
   if [ -n "$lib" ]; then export PPNET_B200_LIB=$PWD/$lib; else unset PPNET_B200_LIB; fi
   echo "== variant ${lib:-default}"; python bench.py --steps 3 --warmup 3 --passes 8 --no-e2e --no-cpu --no-secondary --no-config4 2>/dev/null | python -c "
