@@ -774,7 +774,17 @@ def run_ours(args):
                     "ms_per_step": 1e3 * dt / e2e_steps, "ms_per_pass": 1e3 * dt / n_pass, "steps": e2e_steps,
                     "passes_in_flight": DEPTH, "valid_paths_per_s": M * P * world * e2e_steps / dt}, last, (n_pass - 1) % DEPTH
 
-        e2e, last_map0, ld = e2e_run(checks_up, 20_000)
+        # the region is short (0.7 s) and a shared box has hiccups: run it e2e_repeats times, report the MEDIAN run and list all
+        def e2e_median(checks, base):
+            runs = [e2e_run(checks, base + 1000 * r) for r in range(max(1, args.e2e_repeats))]
+            order = sorted(range(len(runs)), key=lambda r: runs[r][0]["ms_per_pass"])
+            pick = order[len(order) // 2]
+            runs[pick][0]["repeats_ms_per_pass"] = [round(r[0]["ms_per_pass"], 4) for r in runs]
+            runs[pick][0]["repeats_note"] = "median of %d runs of the timed region" % len(runs)
+            # the equality check below needs the LAST run's outputs: they are what the host buffers hold now
+            return runs[pick][0], runs[-1][1], runs[-1][2]
+
+        e2e, last_map0, ld = e2e_median(checks_up, 20_000)
         hw, hout, hvalid_idx, hvalid_cnt = hws[ld], houts[ld], hvalid_idxs[ld], hvalid_cnts[ld]
         # the host results of the last timed pass equal the device-resident path on the same global map range
         chk = ops.generate_maps(bank, last_map0, M, REPS, O, R, MAP_SIZE, OBST_SIZE, CLEAR_UNITS, SEED, raster_inflate=clear_px / 2)
@@ -797,7 +807,7 @@ def run_ours(args):
                            "device, verdicts bit-packed, valid maps compacted) + ppnet_gmm_sample_host (second context, concurrent); "
                            "pinned host buffers",
                     "cpu_affinity": numa_all})
-        e2e_gen, _, _ = e2e_run(checks_gen, 40_000)
+        e2e_gen, _, _ = e2e_median(checks_gen, 40_000)
 
         # the ceiling of this box for these bytes: raw pinned copies of the same volume per pass, both directions at once,
         # every rank at the same time (no kernels, no API of ours) -- at N > 1 the ranks share the host's memory system
@@ -898,6 +908,7 @@ def main():
     ap.add_argument("--cpu-sample-maps", type=int, default=4096, help="maps in the CPU arm's bounded sample (per step / for cpu_baseline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=2, help="host-API passes in flight (one thread + context each)")
+    ap.add_argument("--e2e-repeats", type=int, default=3, help="runs of the e2e timed region; the median is reported, all are listed")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-config1", action="store_true", help="reference arm: skip the 45 s config-1 run of the real reference")
