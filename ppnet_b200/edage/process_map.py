@@ -142,3 +142,142 @@ def extract_path(mask, init_state, end_state, down_sample_rate=8, max_len=4096):
     if not bool(ok.item()):
         return False, None
     return True, out[0, :int(ln.item())].cpu()
+
+
+def extract_path_batch(masks, init_states, end_states, down_sample_rate=8, max_len=4096):
+    """extract_path over many heat-maps of one size in ONE launch: masks = list of PIL images, init / end = [n][2].
+    -> list of (ok, Tensor[L, 2] or None), entry i what `extract_path(masks[i], ...)` returns."""
+    from PIL import Image
+    dev = _dev()
+    n = len(masks)
+    if n == 0:
+        return []
+    small = []
+    for mask in masks:
+        s = mask.resize((int(mask.size[0] / down_sample_rate), int(mask.size[1] / down_sample_rate)), Image.BILINEAR)
+        a = np.asarray(s)
+        a = (a.astype(np.float32) / 255.0) if a.dtype == np.uint8 else a.astype(np.float32)       # ToTensor
+        small.append(a[..., 0] if a.ndim == 3 else a)
+    if any(a.shape != small[0].shape for a in small):
+        raise ops.PPNetError("extract_path_batch: heat-maps of different sizes; call extract_path per image")
+    m = torch.from_numpy(np.ascontiguousarray(np.stack(small))).to(dev)
+    mk = lambda ps: torch.tensor([[float(p[0]), float(p[1])] for p in ps], dtype=torch.float64, device=dev)
+    out, ln, ok = ops.extract_path(m, mk(init_states), mk(end_states), float(down_sample_rate), max_len=max_len)
+    out, ln, ok = out.cpu(), ln.cpu().numpy(), ok.cpu().numpy()
+    return [(True, out[i, :int(ln[i])]) if ok[i] else (False, None) for i in range(n)]
+
+
+def read_folder(root: str = './', is_read_path: bool = True):
+    """process_map.py:75-102: ({root}/*.jpg|png sorted by their numeric stem, the `MapLabel` list torch.save'd under
+    {root}/data, the corridor images under {root}/data as arrays).  A folder that does not hold NUM_PER_FOLDER images is
+    returned unsorted, as the reference does."""
+    import os
+    from PIL import Image
+    spaces_obs = []
+    supported = [".jpg", ".JPG", ".png", ".PNG"]
+    labels = torch.load(r'{}/data/MapLabel'.format(root), weights_only=False)
+    if is_read_path:
+        spaces_folder = r'{}/data'.format(root)
+        images = [i for i in os.listdir(spaces_folder) if os.path.splitext(i)[-1] in supported]
+        for i in list(images):
+            images[int(i[0:-4])] = i
+        for im in images:
+            spaces_obs.append(np.asarray(Image.open(os.path.join(spaces_folder, im))).copy())
+    images = [i for i in os.listdir(root) if os.path.splitext(i)[-1] in supported]
+    if len(images) != NUM_PER_FOLDER:
+        return [os.path.join(root, i) for i in images], labels, spaces_obs
+    for i in list(images):
+        images[int(i[0:-4])] = i
+    images = [os.path.join(root, i) for i in images]
+    return images, labels[0:len(images)], spaces_obs
+
+
+def extract_path_image(mask_root, origin_data_root, result_root, unsolved_problems_txt, clearance, plot=None):
+    """process_map.py:452-506, the caller of A11 on network output: for every heat-map {mask_root}/{index}.png with a
+    matching entry in `unsolved_problems_txt`, extract the waypoints between the map's first and last segment point
+    (`down_sample_rate` 2), reject the path if any edge collides with the problem's obstacles, else append the problem
+    with its `Length` and `Waypoint` to {result_root}/solved_problems.txt -- the same lines in the same order.  All
+    extractions run in one launch per mask size and all edges of all paths in ONE A11 launch (CSR by path).  The
+    reference draws every solution with matplotlib (`plot_solution`); pass `plot=callable(obstacles, path, index)`
+    to do the same.  -> list of failed indices (the reference prints it)."""
+    import json
+    import os
+    from PIL import Image
+    from scipy.spatial import distance
+    with open(unsolved_problems_txt, 'r', encoding='utf-8') as f:
+        unsolved_problems = [json.loads(line) for line in f.readlines()]
+    solved_problems_txt = result_root + "/solved_problems.txt"
+    if not os.path.exists(result_root):
+        os.mkdir(result_root)
+    supported = [".png", ".PNG"]
+    masks = sorted(os.path.join(mask_root, i) for i in os.listdir(mask_root) if os.path.splitext(i)[-1] in supported)
+    by_index = {}
+    for p in unsolved_problems:                     # the reference keeps the FIRST problem with a matching index
+        by_index.setdefault(p["Index"], p)
+    folders = {}
+    jobs = []                                       # (index string, problem, PIL mask, init, end)
+    for m in masks:
+        index = m.split('/')[-1].split('.')[0]
+        problem = by_index.get(int(index))
+        if problem is None:
+            print("No matched problem(Index:{})".format(index))
+            continue
+        folder_index, img_index = int(int(index) / NUM_PER_FOLDER), int(int(index) % NUM_PER_FOLDER)
+        if folder_index not in folders:
+            folders[folder_index] = read_folder(os.path.join(origin_data_root, str(folder_index)), is_read_path=True)
+        images, labels, _ = folders[folder_index]
+        if len(images) != NUM_PER_FOLDER or len(labels) != NUM_PER_FOLDER:
+            continue
+        jobs.append((index, problem, Image.open(m), labels[img_index][3][0], labels[img_index][3][10]))
+    # one extraction launch per mask size
+    results = [None] * len(jobs)
+    by_size = {}
+    for k, j in enumerate(jobs):
+        by_size.setdefault(j[2].size, []).append(k)
+    for ks in by_size.values():
+        got = extract_path_batch([jobs[k][2] for k in ks], [jobs[k][3] for k in ks], [jobs[k][4] for k in ks], down_sample_rate=2)
+        for k, g in zip(ks, got):
+            results[k] = g
+    # every edge of every extracted path against its problem's obstacles: one A11 launch, paths as CSR rows
+    dev = _dev()
+    live = [k for k, r in enumerate(results) if r[0]]
+    blocked = {}
+    if live:
+        omax = max(1, max(len(jobs[k][1]["Obstacles"]) for k in live))
+        obs = torch.zeros([len(live), omax, 3], dtype=torch.float64)
+        cnt = torch.zeros([len(live)], dtype=torch.int32)
+        edges, off = [], [0]
+        for r, k in enumerate(live):
+            o = jobs[k][1]["Obstacles"]
+            if len(o):
+                obs[r, :len(o)] = torch.tensor([[float(v[0]), float(v[1]), float(v[2])] for v in o], dtype=torch.float64)
+            cnt[r] = len(o)
+            p = results[k][1].to(torch.float64)
+            edges.append(torch.cat([p[:-1], p[1:]], dim=1))
+            off.append(off[-1] + len(p) - 1)
+        v = ops.segcheck_edage_f64(torch.cat(edges).contiguous().to(dev), obs.to(dev), cnt.to(dev), float(clearance),
+                                   seg_off=torch.tensor(off, dtype=torch.int64, device=dev)).cpu().numpy()
+        for r, k in enumerate(live):
+            blocked[k] = bool(v[off[r]:off[r + 1]].any())
+    failure_cases = []
+    for k, (index, problem, _, _, _) in enumerate(jobs):
+        rst, path = results[k]
+        if not rst:
+            print("Extract failed:", index)
+            failure_cases.append(index)
+            continue
+        if blocked[k]:
+            failure_cases.append(index)
+            print("Collision:", index)
+            continue
+        print("Planning succeed:", index)
+        length = sum([distance.euclidean(path[i], path[i + 1]) for i in range(len(path) - 1)])
+        problem["Length"] = length
+        problem["Waypoint"] = [list(p) for p in list(path.numpy())]
+        with open(solved_problems_txt, "a") as f:
+            f.write(json.dumps(problem) + "\n")
+        print('cost:', length)
+        if plot is not None:
+            plot(problem["Obstacles"], path, index)
+    print(len(failure_cases), failure_cases)
+    return failure_cases

@@ -679,6 +679,80 @@ def gen_planner_masks():
           "path px", [(m != 0).sum() for m in out["mask_path"]], "values", np.unique(out["mask_space"]), np.unique(out["mask_path"]))
 
 
+def gen_extract_image():
+    """N3's driver, process_map.extract_path_image (:452-506), run through the REAL reference on a four-map dataset the
+    real MapGenerate wrote: heat-maps made from the label paths (one with a gap: extraction fails; one problem gets an
+    extra obstacle on its path: collision), `NUM_PER_FOLDER` set to the dataset's size, `plot_solution` (matplotlib) and
+    the 1 s wall-clock timeout neutralised.  Fixture: the inputs (masks, segment points, problems) and the exact text of
+    solved_problems.txt."""
+    from PIL import Image
+    import json
+    mods = load_edage()
+    MG, pm = mods["MapGenerate"], mods["process_map"]
+    P, O, c, seed = 2, 20, 1, 33
+    tmp = tempfile.mkdtemp(prefix="ppnet_golden_xi_")
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    with quiet():
+        mg = MG.MapGenerate(path_num=P, resolution=224, map_size=50, obstacles_num=O, clearance=c)
+    MG.cnt = 0
+    folder = os.path.join(tmp, "original_data", "0")
+    os.makedirs(os.path.join(tmp, "original_data"))                         # generate() makes the folder, GMM/ and data/ itself
+    with quiet():
+        mg.generate(map_num=P * P, folder_path=folder, round_index=0)
+    n = len(mg.MapLabel)
+    torch.save(mg.MapLabel, os.path.join(folder, "data", "MapLabel"))
+    problems = [json.loads(l) for l in open(os.path.join(tmp, "unsolved_problems.txt"))]
+    assert len(problems) == n and [p["Index"] for p in problems] == list(range(n))
+    segpoints = [np.asarray(l[3], dtype=np.float64) for l in mg.MapLabel]
+    pathpoints = [np.asarray(l[4], dtype=np.float64) for l in mg.MapLabel]
+    # problem 1 gets an obstacle on the middle of its path: its extracted path must be rejected
+    mid = pathpoints[1][len(pathpoints[1]) // 2]
+    problems[1]["Obstacles"].append([float(mid[1]), float(mid[0]), 6.0])
+    utxt = os.path.join(tmp, "unsolved_edit.txt")
+    with open(utxt, "w") as f:
+        for p in problems:
+            f.write(json.dumps(p) + "\n")
+    mask_root = os.path.join(tmp, "masks")
+    os.makedirs(mask_root)
+    heats = []
+    for i in range(n):
+        heat = np.zeros([224, 224], dtype=np.float64)
+        for q in pathpoints[i]:
+            r0, c0 = int(np.round(q[0])), int(np.round(q[1]))
+            for dj in range(-2, 3):
+                for dk in range(-2, 3):
+                    if 0 <= r0 + dj < 224 and 0 <= c0 + dk < 224:
+                        v = 255 - 40 * max(abs(dj), abs(dk)) - (r0 * 7 + c0 * 3) % 23
+                        heat[r0 + dj, c0 + dk] = max(heat[r0 + dj, c0 + dk], v)
+        if i == 2:
+            r_mid = int(np.round(pathpoints[i][len(pathpoints[i]) // 2][0]))
+            heat[max(0, r_mid - 6):r_mid + 6, :] = 0                            # a gap: extraction fails
+        heats.append(heat.astype(np.uint8))
+        Image.fromarray(heats[-1], mode="L").save(os.path.join(mask_root, "%d.png" % i))
+    pm.NUM_PER_FOLDER = n
+    pm.time.time = lambda: 0.0
+    pm.time_synchronized = lambda: 0.0
+    pm.plot_solution = lambda **k: None
+    result_root = os.path.join(tmp, "result")
+    real_load = torch.load                  # the reference predates torch.load's weights_only=True default (torch 2.6)
+    torch.load = lambda *a, **k: real_load(*a, **dict(k, weights_only=False))
+    try:
+        with quiet():
+            pm.extract_path_image(mask_root, os.path.join(tmp, "original_data"), result_root, utxt, c / 50 * 224)
+    finally:
+        torch.load = real_load
+    solved = open(os.path.join(result_root, "solved_problems.txt")).read() if os.path.exists(os.path.join(result_root, "solved_problems.txt")) else ""
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "extract_image.npz"), masks=np.asarray(heats), segpoint=np.asarray(segpoints),
+                        unsolved=np.frombuffer(open(utxt, "rb").read(), dtype=np.uint8),
+                        solved=np.frombuffer(solved.encode(), dtype=np.uint8), clearance=c / 50 * 224)
+    print("extract_image.npz", n, "maps, solved lines:", solved.count("\n"),
+          "indices:", [json.loads(l)["Index"] for l in solved.splitlines()])
+
+
 GENS = {
     # run a second time under OPENBLAS_CORETYPE=HASWELL (set before numpy loads) to pin the un-fused ddot model:
     #   OPENBLAS_CORETYPE=HASWELL python make_golden.py --only segcheck_f64   ->  segcheck_f64_unfused.npz
@@ -691,6 +765,7 @@ GENS = {
     "misc": gen_misc,
     "masks": gen_masks,
     "planner_masks": gen_planner_masks,
+    "extract_image": gen_extract_image,
 }
 
 if __name__ == "__main__":

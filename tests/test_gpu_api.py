@@ -258,6 +258,37 @@ def test_next_rows_placement_label_masks_and_path_extraction(golden, tmp_path):
     assert np.array_equal(v, want_v.astype(bool)) and v.any()
 
 
+def test_extract_path_image_writes_the_references_solved_problems(golden, tmp_path, capsys):
+    """N3's driver (process_map.py:452-506) through the mirror == the file the REAL reference wrote on the same dataset
+    (tests/golden/make_golden.py: gen_extract_image): one path solved per line with its Length and Waypoint list, the
+    collided and the failed extraction left out -- byte for byte."""
+    from PIL import Image
+    from ppnet_b200.edage import process_map
+    g = golden("extract_image")
+    n = len(g["masks"])
+    folder = tmp_path / "original_data" / "0"
+    (folder / "data").mkdir(parents=True)
+    labels = [[None, 0.0, [0, 0], g["segpoint"][i], None] for i in range(n)]
+    torch.save(labels, str(folder / "data" / "MapLabel"))
+    (tmp_path / "masks").mkdir()
+    for i in range(n):
+        Image.fromarray(np.zeros([8, 8, 3], dtype=np.uint8)).save(str(folder / ("%d.jpg" % i)))     # the map images themselves are not read
+        Image.fromarray(g["masks"][i], mode="L").save(str(tmp_path / "masks" / ("%d.png" % i)))
+    Image.fromarray(np.zeros([8, 8, 3], dtype=np.uint8)).save(str(folder / "data" / "0.jpg"))
+    (tmp_path / "unsolved.txt").write_bytes(g["unsolved"].tobytes())
+    old = process_map.NUM_PER_FOLDER
+    process_map.NUM_PER_FOLDER = n
+    try:
+        failed = process_map.extract_path_image(str(tmp_path / "masks"), str(tmp_path / "original_data"), str(tmp_path / "result"),
+                                                str(tmp_path / "unsolved.txt"), float(g["clearance"]))
+    finally:
+        process_map.NUM_PER_FOLDER = old
+    capsys.readouterr()
+    got = (tmp_path / "result" / "solved_problems.txt").read_bytes()
+    assert got == g["solved"].tobytes()
+    assert failed == ["1", "2"]                     # 1: an obstacle sits on its path; 2: the heat-map has a gap
+
+
 def test_planner_solution_masks_vs_reference(golden):
     """N4: the corridor / path label masks of planner solutions == the PNGs the real generated_by_planners wrote."""
     from ppnet_b200 import ops
