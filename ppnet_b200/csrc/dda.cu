@@ -24,6 +24,14 @@ namespace ppnet {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one-lane shared-memory counter bump.  Plain atomicAdd() under `if (lane == 0)` makes the compiler wrap its warp-aggregation
+// sequence (vote, find-leader, popc, shuffle) around an instruction only one lane executes: ~12 instructions per claim.
+__device__ __forceinline__ int smem_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ long long floordiv64(long long num, long long den) {   // den > 0
     return num >= 0 ? num / den : -((den - 1 - num) / den);
 }
@@ -164,7 +172,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
             // compaction of the survivors: ballot scan inside the warp, one shared atomic per warp
             const unsigned wm = __ballot_sync(0xffffffffu, walk);
             int wb = 0;
-            if (lane == 0 && wm) wb = atomicAdd(parked, __popc(wm));
+            if (lane == 0 && wm) wb = smem_add(parked, __popc(wm));
             wb = __shfl_sync(0xffffffffu, wb, 0);
             if (walk) {
                 const bool xmaj = adx >= ady;
@@ -203,7 +211,7 @@ dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict
                     // guided self-scheduling: big claims first, small ones near the end (short tail per warp)
                     const int c = max(8, min(kDdaClaim, (np_ - wend) >> 4));
                     int b = 0;
-                    if (lane == 0) b = atomicAdd(next, c);
+                    if (lane == 0) b = smem_add(next, c);
                     b = __shfl_sync(0xffffffffu, b, 0);
                     wnext = b;
                     wend = min(b + c, np_);
