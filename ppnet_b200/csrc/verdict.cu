@@ -31,6 +31,7 @@ constexpr int kVWarps = kVThreads / 32;
 constexpr int kVQueue = 512;                   // pairs per round of the queue (16 per lane)
 constexpr int kVTake = kVQueue / 32;
 constexpr int kIG = 64;                        // cells per axis of the inner-disk grid (see `inner` in the kernel)
+constexpr int kIGMinSegs = 256;                // CTAs with fewer segments skip the grid
 constexpr int kIGRows = 8;                     // (circle, row) fill tasks per circle and sweep
 
 // smallest float >= t (t finite or inf): (double)x < t  <=>  x < ceil_f32(t) for every float x
@@ -142,7 +143,8 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
     // reference's rounding of the distance (<= 50 u32 Mg, e in [0, bound)^2), the float32 rounding of e and of thr in
     // the float32 flavour, and the float arithmetic of the cell index / the fill below (each <= 1e-6 bound).
     __shared__ uint32_t inner[kIG][kIG / 32];
-    __shared__ float c_rin[kCircTile];            // thr - mg, <= 0: circle takes no part (dead, odd, no grid)
+    __shared__ float c_rin[kCircTile];            // thr - mg, <= 0: circle takes no part (dead, odd, too small, no grid)
+    __shared__ int inner_any;                     // some circle of the tile marks cells: segments look their end point up
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cnt = min(obs_cnt[m], omax);
     const bool use_grid = bound > TIN(0) && bound < TIN(1e6);
@@ -150,7 +152,8 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
 #ifndef PPNET_VINNER
 #define PPNET_VINNER 1
 #endif
-    const bool use_inner = PPNET_VINNER != 0 && use_grid && (float)bound > 1e-6f;       // keeps every product below finite
+    // (bound > 1e-6 keeps every product below finite; a CTA with few segments would not amortise the fill)
+    const bool use_inner = PPNET_VINNER != 0 && use_grid && (float)bound > 1e-6f && (end - base) >= kIGMinSegs;
     const float gs = use_inner ? (float)kIG / (float)bound : 0.0f, cw = (float)bound / (float)kIG;
     const double* __restrict__ mobs = obs + (size_t)m * omax * 3;
 
@@ -180,6 +183,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
             (t < 2 * kBins ? &edge_lo[0][0] : &edge_hi[0][0] - 2 * kBins)[t] = z;
         }
         if (threadIdx.x < 4) { live_mask[threadIdx.x] = 0u; odd_mask[threadIdx.x] = 0u; }
+        if (threadIdx.x == 0) inner_any = 0;
         for (int t = threadIdx.x; t < kIG * kIG / 32; t += kVThreads) (&inner[0][0])[t] = 0u;
         __syncthreads();
         if (threadIdx.x < nt) {
@@ -215,9 +219,12 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     atomicOr(reinterpret_cast<uint32_t*>(&edge_hi[0][x1]) + w, bit);
                     atomicOr(reinterpret_cast<uint32_t*>(&edge_lo[1][y0]) + w, bit);
                     atomicOr(reinterpret_cast<uint32_t*>(&edge_hi[1][y1]) + w, bit);
-                    if (use_inner)
+                    if (use_inner) {
                         rin = (float)thr * 0.999999f -
                               (2.0f * Filt<float>::eps * (2.0f * (float)bound + (float)mc + 1.0f) + 2e-5f * (float)bound);
+                        if (rin > 0.70711f * cw) inner_any = 1;    // a disk of radius < cw / sqrt(2) cannot hold a cell
+                        else rin = -1.0f;
+                    }
                 }
             }
             c_em[j] = em;
@@ -235,7 +242,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                 GT[axis][bin] = acc;
             }
         }
-        if (use_inner) {
+        if (use_inner && inner_any) {
             // inner-disk grid: kIGRows (circle, cell row) tasks per circle and sweep; every rounding shrinks the span
             static_assert(kIG == 64, "one 64-bit span mask per row");
             for (int t = threadIdx.x; t < kIGRows * nt; t += kVThreads) {
@@ -267,6 +274,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
         i = 32 * warp + lane;
 #endif
 
+        const bool look_inner = use_inner && inner_any != 0;
         for (int batch = 32 * warp; batch < n_here; batch += kVThreads) {
             const bool have = i < n_here;
             const int cur = i;
@@ -324,7 +332,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                 if (DO32) p32 = v32 ? (have && v32[cur] != 0) : ((vbits_load(b32, n_words, base + batch) >> lane) & 1u);
                 hit64 = p64 != 0u; hit32 = p32 != 0u;
             }
-            if (use_inner) {                                       // end point inside a disk with margin: blocked, both flavours
+            if (look_inner) {                                      // end point inside a disk with margin: blocked, both flavours
                 const float gx = fe0 * gs, gy = fe1 * gs;
                 if (gx >= 0.0f && gx < (float)kIG && gy >= 0.0f && gy < (float)kIG) {   // (false for NaN)
                     const int ix = (int)gx, iy = (int)gy;

@@ -195,7 +195,7 @@ def test_inner_disk_grid_end_points_around_every_circle_rim(ops, bound):
     corners, circles hanging over the map's border, tiny and huge radii -- a cell marked by mistake would block a
     segment the reference leaves free.  Bit-exact against the C oracle in both flavours and both cmp modes."""
     rng = np.random.default_rng(int(bound * 7))
-    n_maps, omax, spm = 96, 24, 2048
+    n_maps, omax, spm = 1200, 24, 512           # >= 8 x 148 maps: one CTA per map, 512 segments each (the grid needs >= 256)
     obs = np.zeros([n_maps, omax, 3])
     obs[..., 0] = rng.uniform(-0.1 * bound, 1.1 * bound, (n_maps, omax))
     obs[..., 1] = rng.uniform(-0.1 * bound, 1.1 * bound, (n_maps, omax))
