@@ -81,8 +81,11 @@ __device__ __forceinline__ float4 load_seg(const double* segs, int64_t i) {
 // or occupied is blocked whatever happens before (cell_n = the end cell; leaving the map earlier is blocked too), so it is
 // resolved at park time like a blocked start cell: a third fewer segments walk, and the ones that no longer do are the
 // partial walks.
-template <typename TS, bool FIRST>
-__global__ void __launch_bounds__(kDdaThreads)
+// MINB = resident CTAs the register allocation aims at: 4 for small bitmaps (64 registers; measured at config 2: no hint
+// 0.246, 3 -> 0.259, 4 -> 0.232, 5 -> 0.244 ms), 1 for bitmaps that fill shared memory on their own (84 registers, no
+// pressure: config 5 0.349 -> 0.240 ms).
+template <typename TS, bool FIRST, int MINB>
+__global__ void __launch_bounds__(kDdaThreads, MINB)
 dda_kernel(const uint32_t* __restrict__ bits, int R, int W, const TS* __restrict__ segs,
            const int64_t* __restrict__ seg_off, int64_t segs_per_map, int chunk,
            uint8_t* __restrict__ verdict, int32_t* __restrict__ first_hit, uint32_t* __restrict__ vbits,
@@ -315,17 +318,17 @@ static int launch_dda(const uint32_t* bits, int32_t resolution, int64_t n_maps, 
     const int exclusive = (seg_off == nullptr && segs_per_map % 32 == 0) ? 1 : 0;
     if (vbits && !exclusive) PPNET_CUDA(cudaMemsetAsync(vbits, 0, 4 * (size_t)((n_segs + 31) / 32), st));
     dim3 grid((unsigned)n_maps, (unsigned)chunks);
-    if (first_hit) {
-        if (smem > 48 * 1024)
-            PPNET_CUDA(cudaFuncSetAttribute(dda_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dda_kernel<TS, true><<<grid, kDdaThreads, smem, st>>>(bits, resolution, W, segs, seg_off, segs_per_map, chunk, verdict,
-                                                              first_hit, vbits, exclusive);
-    } else {
-        if (smem > 48 * 1024)
-            PPNET_CUDA(cudaFuncSetAttribute(dda_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dda_kernel<TS, false><<<grid, kDdaThreads, smem, st>>>(bits, resolution, W, segs, seg_off, segs_per_map, chunk, verdict,
-                                                               nullptr, vbits, exclusive);
-    }
+#define PPNET_DDA_LAUNCH(F, B)                                                                                              \
+    do {                                                                                                                    \
+        if (smem > 48 * 1024)                                                                                               \
+            PPNET_CUDA(cudaFuncSetAttribute(dda_kernel<TS, F, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dda_kernel<TS, F, B><<<grid, kDdaThreads, smem, st>>>(bits, resolution, W, segs, seg_off, segs_per_map, chunk, verdict,   \
+                                                              F ? first_hit : nullptr, vbits, exclusive);                  \
+    } while (0)
+    const bool big = bm_bytes >= 64 * 1024;                   // at most two such CTAs fit an SM
+    if (first_hit) { if (big) PPNET_DDA_LAUNCH(true, 1); else PPNET_DDA_LAUNCH(true, 4); }
+    else           { if (big) PPNET_DDA_LAUNCH(false, 1); else PPNET_DDA_LAUNCH(false, 4); }
+#undef PPNET_DDA_LAUNCH
     PPNET_LAUNCH_CHECK("dda_kernel");
     return PPNET_OK;
 }
