@@ -108,7 +108,10 @@ struct GenShared {
     int t0, t1, tries, n_acc;
 };
 
-__global__ void __launch_bounds__(kGenThreads)
+#ifndef PPNET_GEN_MINB
+#define PPNET_GEN_MINB 8
+#endif
+__global__ void __launch_bounds__(kGenThreads, PPNET_GEN_MINB)
 generate_kernel(ppnet_gen_params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: odd points [np/2] double2 | hull [hmax] double2 | bitmap [R*W padded to 4] words (optional) |
