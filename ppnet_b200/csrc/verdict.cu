@@ -261,6 +261,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                     const int ix0 = max((int)ceilf((oc.x - hw) * gs + 1e-3f), 0);
                     const int ix1 = min((int)floorf((oc.x + hw) * gs - 1e-3f) - 1, kIG - 1);
                     if (ix0 > ix1) continue;
+                    PPNET_ASSERT(iy >= 0 && iy < kIG && ix0 >= 0 && ix1 < kIG);
                     const unsigned long long span = ((2ull << ix1) - 1ull) & ~((1ull << ix0) - 1ull);   // bits ix0..ix1
                     if ((uint32_t)span) atomicOr(&inner[iy][0], (uint32_t)span);
                     if ((uint32_t)(span >> 32)) atomicOr(&inner[iy][1], (uint32_t)(span >> 32));
@@ -336,6 +337,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
                 const float gx = fe0 * gs, gy = fe1 * gs;
                 if (gx >= 0.0f && gx < (float)kIG && gy >= 0.0f && gy < (float)kIG) {   // (false for NaN)
                     const int ix = (int)gx, iy = (int)gy;
+                    PPNET_ASSERT(ix >= 0 && ix < kIG && iy >= 0 && iy < kIG);
                     if (PPNET_VINNER == 1 && (inner[iy][ix >> 5] >> (ix & 31)) & 1u) hit64 = hit32 = true;
                 }
             }
