@@ -14,6 +14,9 @@ tot = 0
 for it in range(rounds):
     R = int(rng.choice([33, 64, 224, 224, 224, 500, 1024]))
     M = int(rng.integers(1, 400))
+    big = rng.random() < 0.3            # >= 8 x 148 maps: one CTA per map, so CTAs hold >= 256 segments and the verdict
+    if big:                             # kernel's inner-disk grid is on
+        M = int(rng.integers(1200, 2500))
     omax = int(rng.choice([1, 3, 50, 50, 74, 128, 129, 300]))
     clearance = float(rng.choice([0.0, 4.48, 13.44, 1e-9, 40.0])) * R / 224
     bound = float(rng.choice([R, R, R, 0.0, 1e9]))
@@ -21,7 +24,7 @@ for it in range(rounds):
     obs[..., 0] = rng.uniform(-0.1 * R, 1.1 * R, (M, omax)); obs[..., 1] = rng.uniform(-0.1 * R, 1.1 * R, (M, omax))
     obs[..., 2] = rng.uniform(0, rng.choice([0.02, 0.1, 0.3]) * R, (M, omax))
     cnt = rng.integers(0, omax + 1, M).astype(np.int32)
-    per = rng.integers(0, int(rng.choice([3, 40, 600, 3000])), M)
+    per = rng.integers(0, int(rng.choice([3, 40, 600, 3000])), M) if not big else rng.integers(256, 700, M)
     off = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
     n = int(off[-1])
     if n == 0:
