@@ -18,6 +18,10 @@
 //     of shared-memory atomics; "owner already hit" is a register test.
 //   * "exact only" circles / segments are encoded in the data (margin = +inf / L = NaN fall through every filter
 //     comparison into `edge_exact`), no flag words in the pair loop.
+//   * (second half of round 2) an inner-disk grid resolves the segments whose END point lies well inside a circle before
+//     any culling or pair (see `inner` below); the pair decisions are predicated instead of branched and both flavours run
+//     back to back (`fast_pair_bf`); the approximate |d| and 1 / pieces come from one MUFU each; the batches after the
+//     next are prefetched into L2.  DESIGN.md 4.2 has the measurements, including what was tried and dropped.
 #include "segcheck.cuh"
 
 #ifndef PPNET_VBRANCHFREE
