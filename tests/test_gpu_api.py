@@ -289,6 +289,35 @@ def test_extract_path_image_writes_the_references_solved_problems(golden, tmp_pa
     assert failed == ["1", "2"]                     # 1: an obstacle sits on its path; 2: the heat-map has a gap
 
 
+def test_extract_path_image_skips_what_the_reference_skips(golden, tmp_path, capsys):
+    """process_map.py:469-483: a mask without a problem is reported and skipped; a folder that does not hold
+    NUM_PER_FOLDER images is skipped silently; nothing is written when nothing is solved."""
+    from PIL import Image
+    from ppnet_b200.edage import process_map
+    g = golden("extract_image")
+    n = len(g["masks"])
+    folder = tmp_path / "original_data" / "0"
+    (folder / "data").mkdir(parents=True)
+    torch.save([[None, 0.0, [0, 0], g["segpoint"][i], None] for i in range(n)], str(folder / "data" / "MapLabel"))
+    (tmp_path / "masks").mkdir()
+    for i in range(n - 1):                                       # one image short of NUM_PER_FOLDER
+        Image.fromarray(np.zeros([8, 8, 3], dtype=np.uint8)).save(str(folder / ("%d.jpg" % i)))
+    Image.fromarray(np.zeros([8, 8, 3], dtype=np.uint8)).save(str(folder / "data" / "0.jpg"))
+    Image.fromarray(g["masks"][0], mode="L").save(str(tmp_path / "masks" / "0.png"))
+    Image.fromarray(g["masks"][0], mode="L").save(str(tmp_path / "masks" / "77.png"))      # no problem carries index 77
+    (tmp_path / "unsolved.txt").write_bytes(g["unsolved"].tobytes())
+    old = process_map.NUM_PER_FOLDER
+    process_map.NUM_PER_FOLDER = n
+    try:
+        failed = process_map.extract_path_image(str(tmp_path / "masks"), str(tmp_path / "original_data"), str(tmp_path / "result"),
+                                                str(tmp_path / "unsolved.txt"), float(g["clearance"]))
+    finally:
+        process_map.NUM_PER_FOLDER = old
+    out = capsys.readouterr().out
+    assert "No matched problem(Index:77)" in out
+    assert failed == [] and not (tmp_path / "result" / "solved_problems.txt").exists()
+
+
 def test_planner_solution_masks_vs_reference(golden):
     """N4: the corridor / path label masks of planner solutions == the PNGs the real generated_by_planners wrote."""
     from ppnet_b200 import ops

@@ -64,3 +64,38 @@ def test_live_reference_grid_index_and_pathseg(golden):
     m = golden("misc")
     np.testing.assert_allclose(poly, m["seg0_poly"], rtol=1e-9, atol=1e-12)
     assert abs(float(end[0]) - float(m["seg0_end"])) < 1e-12
+
+
+def test_live_reference_read_folder_equals_the_mirror(tmp_path):
+    """process_map.read_folder (:75-102) through the real reference and through the mirror on the same folder: the same
+    image lists (sorted by numeric stem when the folder is complete, as listed otherwise), labels and corridor arrays."""
+    import contextlib, io
+    import torch
+    from PIL import Image
+    from oracle.ref_loader import load_edage
+    from ppnet_b200.edage import process_map as mirror
+    pm = load_edage()["process_map"]
+    folder = tmp_path / "0"
+    (folder / "data").mkdir(parents=True)
+    n = 12                                                       # two-digit stems: string order != numeric order
+    rng = np.random.default_rng(4)
+    for i in range(n):
+        Image.fromarray(rng.integers(0, 255, (6, 6, 3), dtype=np.uint8)).save(str(folder / ("%d.png" % i)))
+    for i in range(2):
+        Image.fromarray(rng.integers(0, 255, (6, 6, 3), dtype=np.uint8)).save(str(folder / "data" / ("%d.png" % i)))
+    torch.save([[i, float(i), [i, i], np.full([11, 2], float(i)), None] for i in range(n + 3)], str(folder / "data" / "MapLabel"))
+    real_load = torch.load                  # the reference predates torch.load's weights_only=True default
+    torch.load = lambda *a, **k: real_load(*a, **dict(k, weights_only=False))
+    old_ref, old_mir = pm.NUM_PER_FOLDER, mirror.NUM_PER_FOLDER
+    try:
+        for per in (n, n + 1):                                   # complete folder / incomplete folder
+            pm.NUM_PER_FOLDER = mirror.NUM_PER_FOLDER = per
+            with contextlib.redirect_stdout(io.StringIO()):
+                want = pm.read_folder(str(folder), is_read_path=True)
+            got = mirror.read_folder(str(folder), is_read_path=True)
+            assert got[0] == want[0]
+            assert len(got[1]) == len(want[1]) and all(a[0] == b[0] for a, b in zip(got[1], want[1]))
+            assert len(got[2]) == len(want[2]) and all(np.array_equal(a, b) for a, b in zip(got[2], want[2]))
+    finally:
+        torch.load = real_load
+        pm.NUM_PER_FOLDER, mirror.NUM_PER_FOLDER = old_ref, old_mir
