@@ -187,7 +187,7 @@ def test_a12_cmp_mode_numpy1_vs_nep50(ops):
             assert orc.segcheck_mpnet_f32(segs32[i, :2], segs32[i, 2:], obs[i].tolist(), CLEAR, cmp_mode=mode) == bool(want[i])
 
 
-@pytest.mark.parametrize("bound", [224.0, 33.0, 100.5, 1024.0])
+@pytest.mark.parametrize("bound", [224.0, 33.0, 100.5, 1024.0, 100000.0, 0.75])
 def test_inner_disk_grid_end_points_around_every_circle_rim(ops, bound):
     """The verdict kernel resolves a segment whose END point lies in a grid cell that is wholly inside a circle's
     threshold disk (verdict.cu, `inner`) without looking at any pair.  Sharp cases for that shortcut: end points at
@@ -206,16 +206,16 @@ def test_inner_disk_grid_end_points_around_every_circle_rim(ops, bound):
     for m in range(n_maps):
         j = rng.integers(0, cnt[m], spm)
         thr = obs[m, j, 2] + clear / 2
-        delta = rng.choice([-1.0, -0.3, -0.12, -0.1, -0.08, -1e-3, -1e-7, 1e-7, 1e-3, 0.5], spm) * rng.uniform(0.5, 1.0, spm)
+        delta = rng.choice([-1.0, -0.3, -0.12, -0.1, -0.08, -1e-3, -1e-7, 1e-7, 1e-3, 0.5], spm) * rng.uniform(0.5, 1.0, spm) * bound / 224
         th = rng.uniform(0, 2 * np.pi, spm)
         ex = obs[m, j, 0] + (thr + delta) * np.cos(th)
         ey = obs[m, j, 1] + (thr + delta) * np.sin(th)
         corner = rng.random(spm) < 0.15                         # end points on (or a hair beside) the 64 x 64 cell corners
-        ex[corner] = np.rint(ex[corner] * 64 / bound) * bound / 64 + rng.choice([0.0, 1e-6, -1e-6], corner.sum())
-        ey[corner] = np.rint(ey[corner] * 64 / bound) * bound / 64 + rng.choice([0.0, 1e-6, -1e-6], corner.sum())
+        ex[corner] = np.rint(ex[corner] * 64 / bound) * bound / 64 + rng.choice([0.0, 1e-6, -1e-6], corner.sum()) * bound / 224
+        ey[corner] = np.rint(ey[corner] * 64 / bound) * bound / 64 + rng.choice([0.0, 1e-6, -1e-6], corner.sum()) * bound / 224
         far = rng.uniform(0, 2 * np.pi, spm)
-        sx = ex + rng.uniform(0.5, bound / 3, spm) * np.cos(far)
-        sy = ey + rng.uniform(0.5, bound / 3, spm) * np.sin(far)
+        sx = ex + rng.uniform(bound / 400, bound / 3, spm) * np.cos(far)
+        sy = ey + rng.uniform(bound / 400, bound / 3, spm) * np.sin(far)
         segs[m] = np.stack([sy, sx, ey, ex], axis=1)            # (row, col) pairs
     segs = segs.reshape(-1, 4)
     segs[::997, 0] = np.nan                                     # a NaN start does not stop the vertex test on e
