@@ -30,7 +30,10 @@
 
 namespace ppnet {
 
-constexpr int kVThreads = 128;
+#ifndef PPNET_VTHREADS
+#define PPNET_VTHREADS 128
+#endif
+constexpr int kVThreads = PPNET_VTHREADS;
 constexpr int kVWarps = kVThreads / 32;
 constexpr int kVQueue = 512;                   // pairs per round of the queue (16 per lane)
 constexpr int kVTake = kVQueue / 32;
@@ -190,8 +193,7 @@ verdict_kernel(const TIN* __restrict__ pts, const int64_t* __restrict__ seg_off,
         if (threadIdx.x == 0) inner_any = 0;
         for (int t = threadIdx.x; t < kIG * kIG / 32; t += kVThreads) (&inner[0][0])[t] = 0u;
         __syncthreads();
-        if (threadIdx.x < nt) {
-            const int j = threadIdx.x;
+        for (int j = threadIdx.x; j < nt; j += kVThreads) {
             const double* o = mobs + 3 * (t0 + j);
             const float oxf = (float)o[0], oyf = (float)o[1];            // torch.tensor([ox, oy]) -> float32 centre
             const double thr = __dadd_rn(o[2], __dmul_rn(clearance, 0.5));   // size + clearance/2 (Python floats; x / 2 == x * 0.5 exactly)
