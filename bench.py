@@ -678,6 +678,9 @@ def run_ours(args):
         if wi:                                               # issue-slot fraction: how close the kernel is to the OTHER ceiling
             k["issue_slot_frac"] = float(wi / (issue_peak * k_ms[i] * 1e-3))
             warp_inst[n] = wi
+        f64 = (traffic.get(n) or {}).get("fp64_pipe_pct")
+        if f64 is not None:                                  # how busy the FP64 pipe is (ncu, same capture) -- not the bound
+            k["fp64_pipe_pct"] = f64
         kernels[n] = k
     dom = names[int(np.argmax(k_ms))]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",

@@ -34,7 +34,8 @@ for r in rows[2:]:
                  lanes_per_instruction=float(r[idx["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
                  smem_wavefronts=int(float(r[idx["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]])),
                  registers=int(float(r[idx["launch__registers_per_thread"]])),
-                 warps_active_pct=float(r[idx["sm__warps_active.avg.pct_of_peak_sustained_active"]]))
+                 warps_active_pct=float(r[idx["sm__warps_active.avg.pct_of_peak_sustained_active"]]),
+                 fp64_pipe_pct=float(r[idx["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]]))
 out["_source"] = "ncu --set full --clock-control none, capture %s (profiles/%s_ncu_full_summary.csv)" % (tag, tag)
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic.json")
 json.dump(out, open(path, "w"), indent=1)
